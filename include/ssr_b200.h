@@ -1,0 +1,129 @@
+/*
+ * ssr_b200 — C ABI of the B200-native embedding-extraction hot path.
+ *
+ * Drop-in boundary for the reference's per-clip extraction calls
+ *   extract_wavlm_embeddings            /root/reference/WavLM_embeddings.py:267-341
+ *   extract_embeddings_from_audio_wavlm /root/reference/model_training_1.py:235-266
+ *   extract_whisper_embeddings_fixed    /root/reference/whisper_embeddings_large.py:234-299 (encoder part)
+ *   extract_embeddings_from_audio_whisper /root/reference/model_training_1.py:268-316       (encoder part)
+ * i.e. for   feature_extractor(audio) -> model(..., output_hidden_states=True) -> torch.mean(h, dim=1)
+ * (WavLM_embeddings.py:289-323, whisper_embeddings_large.py:242-254,272-283).
+ *
+ * Conventions
+ *   - plain C types only; no exceptions cross the boundary; return 0 = OK, negative = error
+ *     (text via ssr_last_error). The Python shim turns any non-zero return into "log + return None",
+ *     which is the reference's error convention (WavLM_embeddings.py:329-341).
+ *   - the caller owns every buffer; the engine owns packed weights and its workspace arena.
+ *   - *_dev entry points are asynchronous on the given CUDA stream (a cudaStream_t passed as void*; NULL =
+ *     legacy default stream) and never synchronise; *_host entry points copy in, run, copy out and
+ *     synchronise the stream before returning.
+ *   - one engine per (process, device); not thread-safe by design (the reference is single-threaded).
+ *   - pooled output layout: float32 [B, L+1, D], layer-major per clip, so pooled[b, i, :] equals
+ *     torch.mean(hidden_states[i], dim=1) of the reference for clip b, for every i in 0..L
+ *     (hidden_states order: HF modeling_wavlm.py:412-439,488-516; modeling_whisper.py:550-553 + output_capturing).
+ */
+#ifndef SSR_B200_H_
+#define SSR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssr_engine ssr_engine;
+
+enum { SSR_WAVLM = 0, SSR_WHISPER_ENC = 1 };
+enum { SSR_FEAT_NORM_GROUP = 0, SSR_FEAT_NORM_LAYER = 1 };
+
+typedef struct ssr_model_desc {
+  int32_t family;       /* SSR_WAVLM | SSR_WHISPER_ENC */
+  int32_t hidden;       /* D: 768 / 1024 (WavLM), 1280 (Whisper-large) */
+  int32_t layers;       /* L */
+  int32_t heads;        /* H, head_dim must be 64 */
+  int32_t ffn;          /* F */
+  int32_t feat_norm;    /* WavLM: SSR_FEAT_NORM_GROUP (Base+) | SSR_FEAT_NORM_LAYER (Large) */
+  int32_t stable_ln;    /* WavLM: config.do_stable_layer_norm */
+  int32_t do_normalize; /* WavLM: Wav2Vec2FeatureExtractor.do_normalize (zero-mean / unit-variance per clip) */
+  int32_t n_mels;       /* Whisper: 80 */
+  int32_t reserved[7];
+} ssr_model_desc;
+
+/* One tensor of the HF state_dict: fp32, contiguous, host memory, named exactly as in model.state_dict().
+ * Whisper additionally takes the feature extractor's filterbank as "mel_filters" ([201, n_mels]). */
+typedef struct ssr_weight {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} ssr_weight;
+
+int ssr_create(const ssr_model_desc* desc, const ssr_weight* weights, int32_t n_weights, int32_t cuda_device,
+               ssr_engine** out);
+void ssr_destroy(ssr_engine* e);
+/* e == NULL returns the message of the last failed ssr_create on this thread's process. */
+const char* ssr_last_error(const ssr_engine* e);
+
+/* Options: "simt_gemm" (bring-up cross-check GEMM), "fused_pool" (default 1), "snapshot_layer" (-1 = off).
+ * Returns 0, or -1 for an unknown key. */
+int ssr_set_option(ssr_engine* e, const char* key, int32_t value);
+
+/* ---- hot path, device buffers --------------------------------------------------------------------------------
+ * audio_dev: float32 [B, audio_ld] (clip b occupies audio_dev[b*audio_ld .. + n_samples[b]); the rest is ignored)
+ * n_samples: HOST int32 [B]
+ * pooled_dev: float32 [B, L+1, D] */
+int ssr_wavlm_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
+                     float* pooled_dev, void* cuda_stream);
+int ssr_whisper_enc_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples,
+                           int32_t B, float* pooled_dev, void* cuda_stream);
+/* Whisper log-mel stage alone: mel_dev float32 [B, n_mels, 3000] (== WhisperFeatureExtractor input_features). */
+int ssr_logmel(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
+               float* mel_dev, void* cuda_stream);
+
+/* ---- hot path, host buffers (the call the drop-in shim makes; H2D and D2H happen inside) -------------------- */
+int ssr_wavlm_pooled_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                          int32_t B, float* pooled_host);
+int ssr_whisper_enc_pooled_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                                int32_t B, float* pooled_host);
+
+/* Number of frames the model produces for a clip of n samples (WavLM conv arithmetic, HF modeling_wavlm.py:647-653;
+ * Whisper: always 1500). */
+int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples);
+/* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
+int64_t ssr_launch_count(const ssr_engine* e);
+/* Device-event time (ms) of the most recent GEMM launches is not tracked here; timing is the caller's job. */
+
+/* ---- stage-level entry points (kernel parity tests; all pointers are device pointers) ------------------------ */
+/* C[M,N] = act(A[M,K] * W[N,K]^T + bias) + resid ; A row r starts at A + r*lda (bf16), rows >= a_rows read zero.
+ * act: 0 none, 1 erf-GELU. out_f32 / out_bf16 / bias / resid may be NULL. simt != 0 selects the debug kernel. */
+int ssr_gemm_bf16(int32_t cuda_device, const void* A, int64_t lda, int64_t a_rows, const void* W, int32_t M,
+                  int32_t N, int32_t K, const float* bias, int32_t act, const float* resid, float* out_f32,
+                  void* out_bf16, int32_t simt, void* cuda_stream, char* err, int32_t err_len);
+/* As above plus fused time mean-pool: rows are clips of `slot` rows of which lens_dev[b] are live;
+ * pooled[b, :] (stride pooled_ld) = mean over live rows of the fp32 result. part_dev: scratch
+ * float32 [ceil(M/32) * 2 * N]. */
+int ssr_gemm_bf16_pool(int32_t cuda_device, const void* A, int64_t lda, const void* W, int32_t M, int32_t N, int32_t K,
+                       const float* bias, int32_t act, const float* resid, float* out_f32, int32_t slot,
+                       const int32_t* lens_dev, int32_t B, float* part_dev, float* pooled_dev, int64_t pooled_ld,
+                       int32_t simt, void* cuda_stream, char* err, int32_t err_len);
+/* LayerNorm over the last dim (eps 1e-5), optional GELU; exactly one of in_f32 / in_bf16. */
+int ssr_layernorm(const float* in_f32, const void* in_bf16, int64_t rows, int32_t D, const float* gamma,
+                  const float* beta, int32_t gelu, float* out_f32, void* out_bf16, void* cuda_stream, char* err,
+                  int32_t err_len);
+/* Self-attention over fused qkv [B*slot, 3*D] bf16 (q pre-scaled), optional WavLM gated relative bias. */
+int ssr_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t slot, int32_t H, const int32_t* lens_dev,
+                  const float* gate, const float* relbias, int32_t rel_stride, int32_t rel_center, void* cuda_stream,
+                  char* err, int32_t err_len);
+/* pooled[b, :] = mean over t < lens[b] of x[b*slot + t, :]. */
+int ssr_pool_mean(const float* x, int32_t B, int32_t slot, int32_t D, const int32_t* lens_dev, float* pooled,
+                  int64_t pooled_ld, void* cuda_stream, char* err, int32_t err_len);
+
+/* ---- debug taps: copy a named internal buffer of the last run to host (synchronises). Returns bytes copied,
+ * or a negative error. With dst == NULL returns the buffer's size in bytes. `dims` (optional, 4 entries) gets the
+ * logical shape, `dtype` (optional) 0 = float32, 1 = bfloat16. */
+int64_t ssr_debug_fetch(ssr_engine* e, const char* name, void* dst_host, int64_t dst_bytes, int64_t* dims,
+                        int32_t* dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSR_B200_H_ */

@@ -1,0 +1,19 @@
+"""B200-native embedding-extraction hot path (WavLM / Whisper-encoder per-layer pooled embeddings).
+
+The directory name mirrors the upstream repository; import it as `ssr_b200` (see /ssr_b200/__init__.py).
+"""
+from .engine import SsrError, WavLMEngine, WhisperEncoderEngine, iter_batches, shard_range  # noqa: F401
+from .extract import (  # noqa: F401
+    extract_embeddings_from_audio_wavlm,
+    extract_embeddings_from_audio_whisper,
+    extract_wavlm_embeddings,
+    extract_whisper_embeddings_fixed,
+    get_engine,
+    pooled_to_layer_dict,
+)
+
+__all__ = [
+    "SsrError", "WavLMEngine", "WhisperEncoderEngine", "iter_batches", "shard_range",
+    "extract_wavlm_embeddings", "extract_embeddings_from_audio_wavlm", "extract_whisper_embeddings_fixed",
+    "extract_embeddings_from_audio_whisper", "get_engine", "pooled_to_layer_dict",
+]

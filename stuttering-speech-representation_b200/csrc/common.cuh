@@ -1,0 +1,60 @@
+// Shared host/device declarations for the ssr_b200 kernels (internal; the public C ABI is include/ssr_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+namespace ssr {
+
+typedef __nv_bfloat16 bf16;
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1 };
+
+// Epilogue applied to every GEMM output element  acc[r, c]  (r = flat A row, c = output column):
+//   v = act(acc + bias[c]) + resid[...]
+// and the row is routed through a slot remap, which is how padded / strided per-clip layouts are compacted:
+//   b = r / in_slot, t = r % in_slot;  row is live iff t < (lens ? lens[b] : valid)
+//   out_row = b * out_slot + t + out_off
+// resid is indexed by out_row (resid_by_t == 0) or by t (resid_by_t == 1, e.g. a positional table).
+struct EpiParams {
+  const float* bias;
+  const float* resid;
+  float* out_f32;
+  bf16* out_bf16;
+  const int* lens;
+  int ldr, ldo32, ldo16;
+  int act;
+  int in_slot, out_slot, valid, out_off;  // in_slot == 0: identity mapping, all rows < M live
+  int resid_by_t;
+  // fused time mean-pool: per 32-row group and segment (0: clip of the group's first row, 1: the next clip)
+  // column sums are written to pool_part[(group * 2 + seg) * N + c]; a finalize kernel reduces them in fixed order.
+  float* pool_part;
+  int pool_slot;  // rows per clip in OUTPUT row space (live rows only are summed)
+};
+
+struct GemmParams {
+  int M, N, K;
+  int a_mode;  // 0: A[r, k] plain (tensor map {K, M});  1: positional conv, A[r, tap*64 + c] = X[r + tap, ntile*64 + c]
+  int num_m_tiles, num_n_tiles, num_kb;
+  EpiParams epi;
+};
+
+struct GemmOp {
+  const bf16* A;
+  long long lda;  // elements between consecutive A rows (may be < K: overlapping conv windows)
+  long long a_rows;  // rows addressable in A (tensor-map bound; rows >= a_rows read as zero)
+  const bf16* W;  // [N, K] row-major
+  int M, N, K;
+  int a_mode;
+  int a_cols;  // a_mode 1: width (channels) of X
+  EpiParams epi;
+};
+
+// ---- launchers (each returns cudaError_t / sets message in err) ----
+int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace ssr

@@ -1,0 +1,1325 @@
+// Model drivers + the C ABI (include/ssr_b200.h).  Host-side C++: weight packing from HF state_dict tensors,
+// workspace arena, the WavLM / Whisper-encoder layer loops, fused per-layer time pooling.
+//
+// Reference call stacks being replaced:
+//   WavLMModel.forward          HF/models/wavlm/modeling_wavlm.py:1039-1095  (feature encoder :779-789, projection :100-105,
+//                               encoder :388-447 / :465-522, layers :314-373)
+//   WhisperEncoder.forward      HF/models/whisper/modeling_whisper.py:593-647 (layer :380-414, attention :284-357)
+//   pooling                     REF/WavLM_embeddings.py:321, REF/whisper_embeddings_large.py:278
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ssr_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace ssr;
+
+namespace {
+
+std::string g_create_error;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t ce__ = (call);                                                                    \
+    if (ce__ != cudaSuccess) {                                                                    \
+      err = std::string(#call) + ": " + cudaGetErrorString(ce__);                                 \
+      return -1;                                                                                  \
+    }                                                                                             \
+  } while (0)
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);                                            // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~Buf() {
+    if (p) cudaFree(p);
+  }
+  // Grow-only; new memory is zero-filled (padding regions rely on it and are never written afterwards).
+  int ensure(size_t bytes, cudaStream_t st, std::string& err) {
+    if (bytes <= cap) return 0;
+    if (p) {
+      CK(cudaStreamSynchronize(st));
+      CK(cudaFree(p));
+      p = nullptr;
+      cap = 0;
+    }
+    bytes = (bytes + 255) & ~size_t(255);
+    CK(cudaMalloc(&p, bytes));
+    CK(cudaMemsetAsync(p, 0, bytes, st));
+    cap = bytes;
+    return 0;
+  }
+  template <typename T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct DbgBuf {
+  const void* p;
+  int64_t bytes;
+  int64_t dims[4];
+  int32_t dtype;
+};
+
+struct LayerW {
+  bf16 *wqkv, *wo, *w1, *w2;
+  float *bqkv, *bo, *b1, *b2;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  float *gate_wa, *gate_wb, *gate_const;
+  float gate_ba, gate_bb;
+};
+
+}  // namespace
+
+struct ssr_engine {
+  ssr_model_desc d;
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  int64_t launches = 0;
+  // options
+  int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1;
+
+  // ---- weights (device) ----
+  std::vector<void*> owned;  // every cudaMalloc'd weight block
+  // WavLM front end
+  float* c0_w = nullptr;
+  float *cln_g[7] = {}, *cln_b[7] = {};
+  bf16* conv_w[7] = {};
+  float *fp_ln_g = nullptr, *fp_ln_b = nullptr, *fp_b = nullptr;
+  bf16* fp_w = nullptr;
+  bf16* pos_w = nullptr;
+  float* pos_b = nullptr;
+  float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
+  std::vector<float> rel_embed_host;  // [320, H]
+  Buf relbias;
+  int rel_R = 0;
+  // Whisper front end
+  float *twiddle = nullptr, *melw = nullptr;
+  int *mel_lo = nullptr, *mel_hi = nullptr;
+  bf16 *wc1 = nullptr, *wc2 = nullptr;
+  float *bc1 = nullptr, *bc2 = nullptr, *pos_emb = nullptr;
+  std::vector<LayerW> layers;
+
+  // ---- workspace ----
+  Buf nsamp_dev, lens_dev, stats, gn_acc;
+  Buf conv[7], feat_ln, feat, xp, posconv, h, tmp, xn, qkv, ctx, mid, gate, pool_part;
+  Buf logspec, gmax, conv_in, c1, lens1500;
+  Buf audio_stage, pooled_stage;
+  Buf snap[8];
+  std::map<std::string, DbgBuf> dbg;
+
+  ~ssr_engine() {
+    for (void* p : owned) cudaFree(p);
+  }
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ weight access
+struct WeightMap {
+  std::map<std::string, const ssr_weight*> m;
+  std::string err;
+  const float* get(const std::string& name, int64_t numel) {
+    auto it = m.find(name);
+    if (it == m.end()) it = m.find("encoder." + name);
+    if (it == m.end()) {
+      if (err.empty()) err = "missing weight '" + name + "'";
+      return nullptr;
+    }
+    if (it->second->numel != numel) {
+      if (err.empty())
+        err = "weight '" + name + "' has " + std::to_string(it->second->numel) + " elements, expected " +
+              std::to_string(numel);
+      return nullptr;
+    }
+    return it->second->data;
+  }
+  bool has(const std::string& name) { return m.count(name) || m.count("encoder." + name); }
+};
+
+template <typename T>
+int upload(ssr_engine* e, const std::vector<T>& host, T** dev, std::string& err) {
+  void* p = nullptr;
+  CK(cudaMalloc(&p, host.size() * sizeof(T) + 16));
+  CK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  e->owned.push_back(p);
+  *dev = reinterpret_cast<T*>(p);
+  return 0;
+}
+int upload_f32(ssr_engine* e, const float* src, int64_t n, float** dev, std::string& err) {
+  if (!src) return -1;
+  std::vector<float> v(src, src + n);
+  return upload(e, v, dev, err);
+}
+int upload_bf16(ssr_engine* e, const float* src, int64_t n, float scale, bf16** dev, std::string& err) {
+  if (!src) return -1;
+  std::vector<uint16_t> v((size_t)n);
+  for (int64_t i = 0; i < n; ++i) v[i] = f2bf(src[i] * scale);
+  uint16_t* d = nullptr;
+  if (upload(e, v, &d, err)) return -1;
+  *dev = reinterpret_cast<bf16*>(d);
+  return 0;
+}
+
+// Fused [3D, D] q/k/v weight (q rows pre-scaled by head_dim^-0.5 = 1/8, exact in bf16) and [3D] bias.
+int pack_qkv(ssr_engine* e, WeightMap& w, const std::string& pq, const std::string& pk, const std::string& pv, int D,
+             bool k_has_bias, LayerW& L, std::string& err) {
+  const float* wq = w.get(pq + ".weight", (int64_t)D * D);
+  const float* wk = w.get(pk + ".weight", (int64_t)D * D);
+  const float* wv = w.get(pv + ".weight", (int64_t)D * D);
+  const float* bq = w.get(pq + ".bias", D);
+  const float* bk = k_has_bias ? w.get(pk + ".bias", D) : nullptr;
+  const float* bv = w.get(pv + ".bias", D);
+  if (!wq || !wk || !wv || !bq || !bv || (k_has_bias && !bk)) return -1;
+  std::vector<uint16_t> W((size_t)3 * D * D);
+  const size_t DD = (size_t)D * D;
+  for (size_t i = 0; i < DD; ++i) {
+    W[i] = f2bf(wq[i] * 0.125f);
+    W[DD + i] = f2bf(wk[i]);
+    W[2 * DD + i] = f2bf(wv[i]);
+  }
+  std::vector<float> B((size_t)3 * D, 0.f);
+  for (int i = 0; i < D; ++i) {
+    B[i] = bq[i] * 0.125f;
+    B[D + i] = bk ? bk[i] : 0.f;
+    B[2 * D + i] = bv[i];
+  }
+  uint16_t* dW = nullptr;
+  if (upload(e, W, &dW, err)) return -1;
+  L.wqkv = reinterpret_cast<bf16*>(dW);
+  return upload(e, B, &L.bqkv, err);
+}
+
+// Conv1d weight [Co, Ci, k] -> implicit-GEMM weight [Co, k*Ci] (tap-major, matching channels-last im2col rows).
+int pack_conv(ssr_engine* e, const float* w, int Co, int Ci, int k, bf16** dev, std::string& err) {
+  if (!w) return -1;
+  std::vector<uint16_t> W((size_t)Co * Ci * k);
+  for (int co = 0; co < Co; ++co)
+    for (int ci = 0; ci < Ci; ++ci)
+      for (int t = 0; t < k; ++t) W[((size_t)co * k + t) * Ci + ci] = f2bf(w[((size_t)co * Ci + ci) * k + t]);
+  uint16_t* d = nullptr;
+  if (upload(e, W, &d, err)) return -1;
+  *dev = reinterpret_cast<bf16*>(d);
+  return 0;
+}
+
+// HF WavLMAttention._relative_positions_bucket (modeling_wavlm.py:252-271), num_buckets 320, max_distance 800.
+int rel_bucket(int rel) {
+  const int nb = 160, max_exact = 80;
+  int bucket = rel > 0 ? nb : 0;
+  const int a = rel < 0 ? -rel : rel;
+  if (a < max_exact) return bucket + a;
+  float v = logf((float)a / (float)max_exact);
+  v = v / (float)log(800.0 / 80.0);
+  v = v * (float)(nb - max_exact);
+  long large = (long)((float)max_exact + v);
+  if (large > nb - 1) large = nb - 1;
+  return bucket + (int)large;
+}
+
+int build_relbias(ssr_engine* e, int R, cudaStream_t st, std::string& err) {
+  if (R <= e->rel_R) return 0;
+  int newR = 256;
+  while (newR < R) newR *= 2;
+  const int H = e->d.heads, W = 2 * newR - 1;
+  std::vector<float> tab((size_t)H * W);
+  for (int rel = -(newR - 1); rel <= newR - 1; ++rel) {
+    const int bkt = rel_bucket(rel);
+    for (int h = 0; h < H; ++h) tab[(size_t)h * W + rel + newR - 1] = e->rel_embed_host[(size_t)bkt * H + h];
+  }
+  if (e->relbias.ensure(tab.size() * 4, st, err)) return -1;
+  CK(cudaMemcpyAsync(e->relbias.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  e->rel_R = newR;
+  return 0;
+}
+
+int create_wavlm(ssr_engine* e, WeightMap& w, std::string& err) {
+  const ssr_model_desc& d = e->d;
+  const int D = d.hidden, F = d.ffn, H = d.heads, L = d.layers;
+  if (D != H * 64) {
+    err = "WavLM: head_dim must be 64";
+    return -1;
+  }
+  if (D % 128 != 0 || D / 16 > 64) {
+    err = "WavLM: unsupported hidden size";
+    return -1;
+  }
+  static const int ks[7] = {10, 3, 3, 3, 3, 2, 2};
+  const bool layer_norm = d.feat_norm == SSR_FEAT_NORM_LAYER;
+  if (upload_f32(e, w.get("feature_extractor.conv_layers.0.conv.weight", 5120), 5120, &e->c0_w, err)) return -1;
+  for (int i = 0; i < 7; ++i) {
+    const std::string p = "feature_extractor.conv_layers." + std::to_string(i);
+    if (i > 0 && pack_conv(e, w.get(p + ".conv.weight", 512LL * 512 * ks[i]), 512, 512, ks[i], &e->conv_w[i], err))
+      return -1;
+    if (layer_norm || i == 0) {
+      if (upload_f32(e, w.get(p + ".layer_norm.weight", 512), 512, &e->cln_g[i], err)) return -1;
+      if (upload_f32(e, w.get(p + ".layer_norm.bias", 512), 512, &e->cln_b[i], err)) return -1;
+    }
+  }
+  if (upload_f32(e, w.get("feature_projection.layer_norm.weight", 512), 512, &e->fp_ln_g, err)) return -1;
+  if (upload_f32(e, w.get("feature_projection.layer_norm.bias", 512), 512, &e->fp_ln_b, err)) return -1;
+  if (upload_bf16(e, w.get("feature_projection.projection.weight", 512LL * D), 512LL * D, 1.f, &e->fp_w, err))
+    return -1;
+  if (upload_f32(e, w.get("feature_projection.projection.bias", D), D, &e->fp_b, err)) return -1;
+  {
+    // weight-norm (dim = 2): w[co, ci, k] = g[k] * v[co, ci, k] / ||v[:, :, k]||   (modeling_wavlm.py:59-77)
+    const int gw = D / 16;
+    const float* g = w.get("encoder.pos_conv_embed.conv.parametrizations.weight.original0", 128);
+    const float* v = w.get("encoder.pos_conv_embed.conv.parametrizations.weight.original1", (int64_t)D * gw * 128);
+    if (!g || !v) return -1;
+    std::vector<double> nrm(128, 0.0);
+    for (int64_t i = 0; i < (int64_t)D * gw; ++i)
+      for (int k = 0; k < 128; ++k) nrm[k] += (double)v[i * 128 + k] * (double)v[i * 128 + k];
+    std::vector<float> sc(128);
+    for (int k = 0; k < 128; ++k) sc[k] = (float)((double)g[k] / sqrt(nrm[k]));
+    std::vector<uint16_t> W((size_t)1024 * 8192, 0);
+    for (int grp = 0; grp < 16; ++grp)
+      for (int co = 0; co < gw; ++co)
+        for (int ci = 0; ci < gw; ++ci)
+          for (int k = 0; k < 128; ++k)
+            W[((size_t)(grp * 64 + co)) * 8192 + k * 64 + ci] =
+                f2bf(v[(((size_t)(grp * gw + co)) * gw + ci) * 128 + k] * sc[k]);
+    uint16_t* dW = nullptr;
+    if (upload(e, W, &dW, err)) return -1;
+    e->pos_w = reinterpret_cast<bf16*>(dW);
+    if (upload_f32(e, w.get("encoder.pos_conv_embed.conv.bias", D), D, &e->pos_b, err)) return -1;
+  }
+  if (upload_f32(e, w.get("encoder.layer_norm.weight", D), D, &e->enc_ln_g, err)) return -1;
+  if (upload_f32(e, w.get("encoder.layer_norm.bias", D), D, &e->enc_ln_b, err)) return -1;
+  {
+    const float* re = w.get("encoder.layers.0.attention.rel_attn_embed.weight", 320LL * H);
+    if (!re) return -1;
+    e->rel_embed_host.assign(re, re + 320LL * H);
+  }
+  e->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    LayerW& Lw = e->layers[l];
+    const std::string p = "encoder.layers." + std::to_string(l);
+    if (pack_qkv(e, w, p + ".attention.q_proj", p + ".attention.k_proj", p + ".attention.v_proj", D, true, Lw, err))
+      return -1;
+    if (upload_bf16(e, w.get(p + ".attention.out_proj.weight", (int64_t)D * D), (int64_t)D * D, 1.f, &Lw.wo, err))
+      return -1;
+    if (upload_f32(e, w.get(p + ".attention.out_proj.bias", D), D, &Lw.bo, err)) return -1;
+    if (upload_f32(e, w.get(p + ".layer_norm.weight", D), D, &Lw.ln1_g, err)) return -1;
+    if (upload_f32(e, w.get(p + ".layer_norm.bias", D), D, &Lw.ln1_b, err)) return -1;
+    if (upload_bf16(e, w.get(p + ".feed_forward.intermediate_dense.weight", (int64_t)F * D), (int64_t)F * D, 1.f,
+                    &Lw.w1, err))
+      return -1;
+    if (upload_f32(e, w.get(p + ".feed_forward.intermediate_dense.bias", F), F, &Lw.b1, err)) return -1;
+    if (upload_bf16(e, w.get(p + ".feed_forward.output_dense.weight", (int64_t)D * F), (int64_t)D * F, 1.f, &Lw.w2,
+                    err))
+      return -1;
+    if (upload_f32(e, w.get(p + ".feed_forward.output_dense.bias", D), D, &Lw.b2, err)) return -1;
+    if (upload_f32(e, w.get(p + ".final_layer_norm.weight", D), D, &Lw.ln2_g, err)) return -1;
+    if (upload_f32(e, w.get(p + ".final_layer_norm.bias", D), D, &Lw.ln2_b, err)) return -1;
+    const float* gw8 = w.get(p + ".attention.gru_rel_pos_linear.weight", 8 * 64);
+    const float* gb8 = w.get(p + ".attention.gru_rel_pos_linear.bias", 8);
+    const float* gc = w.get(p + ".attention.gru_rel_pos_const", H);
+    if (!gw8 || !gb8 || !gc) return -1;
+    std::vector<float> wa(64, 0.f), wb(64, 0.f);
+    for (int j = 0; j < 64; ++j) {
+      wa[j] = (gw8[0 * 64 + j] + gw8[1 * 64 + j]) + (gw8[2 * 64 + j] + gw8[3 * 64 + j]);
+      wb[j] = (gw8[4 * 64 + j] + gw8[5 * 64 + j]) + (gw8[6 * 64 + j] + gw8[7 * 64 + j]);
+    }
+    Lw.gate_ba = (gb8[0] + gb8[1]) + (gb8[2] + gb8[3]);
+    Lw.gate_bb = (gb8[4] + gb8[5]) + (gb8[6] + gb8[7]);
+    if (upload(e, wa, &Lw.gate_wa, err)) return -1;
+    if (upload(e, wb, &Lw.gate_wb, err)) return -1;
+    if (upload_f32(e, gc, H, &Lw.gate_const, err)) return -1;
+  }
+  return 0;
+}
+
+int create_whisper(ssr_engine* e, WeightMap& w, std::string& err) {
+  const ssr_model_desc& d = e->d;
+  const int D = d.hidden, F = d.ffn, H = d.heads, L = d.layers, NM = d.n_mels;
+  if (D != H * 64 || D % 256 != 0) {
+    err = "Whisper: head_dim must be 64 and d_model a multiple of 256";
+    return -1;
+  }
+  if (NM != 80) {
+    err = "Whisper: only 80 mel bins are supported (whisper-large v1/v2, small, base, ...)";
+    return -1;
+  }
+  // hann-windowed DFT table: column 2f = w[k] cos(2 pi f k / 400), 2f+1 = -w[k] sin(...), periodic hann.
+  {
+    std::vector<float> tw((size_t)400 * 448, 0.f);
+    const double PI = 3.14159265358979323846;
+    for (int k = 0; k < 400; ++k) {
+      const double win = 0.5 - 0.5 * cos(2.0 * PI * k / 400.0);
+      for (int f = 0; f < 201; ++f) {
+        const int ph = (int)(((long long)f * k) % 400);
+        const double ang = 2.0 * PI * ph / 400.0;
+        tw[(size_t)k * 448 + 2 * f] = (float)(win * cos(ang));
+        tw[(size_t)k * 448 + 2 * f + 1] = (float)(-win * sin(ang));
+      }
+    }
+    if (upload(e, tw, &e->twiddle, err)) return -1;
+    const float* mf = w.get("mel_filters", 201LL * NM);  // [201, 80] as WhisperFeatureExtractor.mel_filters
+    if (!mf) return -1;
+    std::vector<float> mw((size_t)NM * 201);
+    std::vector<int> lo(NM), hi(NM);
+    for (int m = 0; m < NM; ++m) {
+      lo[m] = 201;
+      hi[m] = -1;
+      for (int f = 0; f < 201; ++f) {
+        const float v = mf[(size_t)f * NM + m];
+        mw[(size_t)m * 201 + f] = v;
+        if (v != 0.f) {
+          if (f < lo[m]) lo[m] = f;
+          hi[m] = f;
+        }
+      }
+      if (hi[m] < 0) {
+        lo[m] = 0;
+        hi[m] = -1;
+      }
+    }
+    if (upload(e, mw, &e->melw, err)) return -1;
+    if (upload(e, lo, &e->mel_lo, err)) return -1;
+    if (upload(e, hi, &e->mel_hi, err)) return -1;
+  }
+  if (pack_conv(e, w.get("conv1.weight", (int64_t)D * NM * 3), D, NM, 3, &e->wc1, err)) return -1;
+  if (upload_f32(e, w.get("conv1.bias", D), D, &e->bc1, err)) return -1;
+  if (pack_conv(e, w.get("conv2.weight", (int64_t)D * D * 3), D, D, 3, &e->wc2, err)) return -1;
+  if (upload_f32(e, w.get("conv2.bias", D), D, &e->bc2, err)) return -1;
+  if (upload_f32(e, w.get("embed_positions.weight", 1500LL * D), 1500LL * D, &e->pos_emb, err)) return -1;
+  if (upload_f32(e, w.get("layer_norm.weight", D), D, &e->enc_ln_g, err)) return -1;
+  if (upload_f32(e, w.get("layer_norm.bias", D), D, &e->enc_ln_b, err)) return -1;
+  e->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    LayerW& Lw = e->layers[l];
+    memset(&Lw, 0, sizeof(Lw));
+    const std::string p = "layers." + std::to_string(l);
+    if (pack_qkv(e, w, p + ".self_attn.q_proj", p + ".self_attn.k_proj", p + ".self_attn.v_proj", D, false, Lw, err))
+      return -1;
+    if (upload_bf16(e, w.get(p + ".self_attn.out_proj.weight", (int64_t)D * D), (int64_t)D * D, 1.f, &Lw.wo, err))
+      return -1;
+    if (upload_f32(e, w.get(p + ".self_attn.out_proj.bias", D), D, &Lw.bo, err)) return -1;
+    if (upload_f32(e, w.get(p + ".self_attn_layer_norm.weight", D), D, &Lw.ln1_g, err)) return -1;
+    if (upload_f32(e, w.get(p + ".self_attn_layer_norm.bias", D), D, &Lw.ln1_b, err)) return -1;
+    if (upload_bf16(e, w.get(p + ".fc1.weight", (int64_t)F * D), (int64_t)F * D, 1.f, &Lw.w1, err)) return -1;
+    if (upload_f32(e, w.get(p + ".fc1.bias", F), F, &Lw.b1, err)) return -1;
+    if (upload_bf16(e, w.get(p + ".fc2.weight", (int64_t)D * F), (int64_t)D * F, 1.f, &Lw.w2, err)) return -1;
+    if (upload_f32(e, w.get(p + ".fc2.bias", D), D, &Lw.b2, err)) return -1;
+    if (upload_f32(e, w.get(p + ".final_layer_norm.weight", D), D, &Lw.ln2_g, err)) return -1;
+    if (upload_f32(e, w.get(p + ".final_layer_norm.bias", D), D, &Lw.ln2_b, err)) return -1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ step helpers
+EpiParams epi_plain(const float* bias, int act, const float* resid, int ldr, float* o32, int ld32, bf16* o16,
+                    int ld16) {
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias;
+  ep.act = act;
+  ep.resid = resid;
+  ep.ldr = ldr;
+  ep.out_f32 = o32;
+  ep.ldo32 = ld32;
+  ep.out_bf16 = o16;
+  ep.ldo16 = ld16;
+  return ep;
+}
+
+int run_gemm(ssr_engine* e, const GemmOp& op, cudaStream_t st) {
+  e->launches += e->opt_simt ? (op.epi.pool_part ? 2 : 1) : 1;
+  return launch_gemm(op, st, e->opt_simt != 0, e->num_sms, e->err);
+}
+
+GemmOp linear_op(const bf16* A, int M, int K, const bf16* W, int N, const EpiParams& ep) {
+  GemmOp op;
+  op.A = A;
+  op.lda = K;
+  op.a_rows = M;
+  op.W = W;
+  op.M = M;
+  op.N = N;
+  op.K = K;
+  op.a_mode = 0;
+  op.a_cols = 0;
+  op.epi = ep;
+  return op;
+}
+
+void reg_dbg(ssr_engine* e, const char* name, const void* p, int dtype, int64_t d0, int64_t d1, int64_t d2 = 1,
+             int64_t d3 = 1) {
+  DbgBuf b;
+  b.p = p;
+  b.dtype = dtype;
+  b.dims[0] = d0;
+  b.dims[1] = d1;
+  b.dims[2] = d2;
+  b.dims[3] = d3;
+  b.bytes = d0 * d1 * d2 * d3 * (dtype == 0 ? 4 : 2);
+  e->dbg[name] = b;
+}
+
+int snapshot(ssr_engine* e, int slot_idx, const char* name, const void* src, int dtype, int64_t rows, int64_t cols,
+             cudaStream_t st) {
+  std::string& err = e->err;
+  const size_t bytes = (size_t)rows * cols * (dtype == 0 ? 4 : 2);
+  if (e->snap[slot_idx].ensure(bytes, st, err)) return -1;
+  CK(cudaMemcpyAsync(e->snap[slot_idx].p, src, bytes, cudaMemcpyDeviceToDevice, st));
+  reg_dbg(e, name, e->snap[slot_idx].p, dtype, rows, cols);
+  return 0;
+}
+
+int wavlm_frames(int n) {
+  static const int ks[7] = {10, 3, 3, 3, 3, 2, 2}, ss[7] = {5, 2, 2, 2, 2, 2, 2};
+  long long len = n;
+  for (int i = 0; i < 7; ++i) {
+    if (len < ks[i]) return 0;
+    len = (len - ks[i]) / ss[i] + 1;
+  }
+  return (int)len;
+}
+
+int pool_into(ssr_engine* e, const float* x, int B, int slot, int D, float* pooled, int layer, int L1,
+              cudaStream_t st) {
+  e->launches += 1;
+  return launch_pool_mean(x, B, slot, D, e->lens_dev.as<int>(), pooled + (long long)layer * D, (long long)L1 * D, st,
+                          e->err);
+}
+
+// One transformer layer stack shared by WavLM (both LayerNorm placements) and Whisper.
+//   pre_ln  (WavLM-Large "stable", Whisper): h += Attn(LN1(h)); h += FFN(LN2(h))
+//   post_ln (WavLM-Base+):                   h = LN1(h + Attn(h)); h = LN2(h + FFN(h))
+int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* pooled, cudaStream_t st) {
+  std::string& err = e->err;
+  const int D = e->d.hidden, F = e->d.ffn, H = e->d.heads, L = e->d.layers, L1 = L + 1;
+  const int M = B * slot;
+  const int* lens = e->lens_dev.as<int>();
+  float* h = e->h.as<float>();
+  float* tmp = e->tmp.as<float>();
+  bf16* xn = e->xn.as<bf16>();
+  bf16* qkv = e->qkv.as<bf16>();
+  bf16* ctx = e->ctx.as<bf16>();
+  bf16* mid = e->mid.as<bf16>();
+  float* gate = wavlm ? e->gate.as<float>() : nullptr;
+  float* part = e->pool_part.as<float>();
+  const bool fused = e->opt_fused_pool && slot >= 32;
+
+  for (int l = 0; l < L; ++l) {
+    const LayerW& W = e->layers[l];
+    const bool snap = (e->opt_snapshot_layer == l);
+    if (pre_ln) {
+      LayerNormArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in_f32 = h;
+      a.rows = M;
+      a.D = D;
+      a.ld_in = D;
+      a.gamma = W.ln1_g;
+      a.beta = W.ln1_b;
+      a.eps = 1e-5f;
+      a.out_bf16 = xn;
+      a.ld_out16 = D;
+      if (wavlm) {
+        a.gate_out = gate;
+        a.gate_wa = W.gate_wa;
+        a.gate_wb = W.gate_wb;
+        a.gate_ba = W.gate_ba;
+        a.gate_bb = W.gate_bb;
+        a.gate_const = W.gate_const;
+        a.n_heads = H;
+      }
+      e->launches++;
+      if (launch_layernorm(a, st, err)) return -1;
+    }
+    // (post-LN: xn / gate for this layer were produced by the previous LayerNorm)
+    if (snap && snapshot(e, 0, "L.attn_in", xn, 1, M, D, st)) return -1;
+    if (snap && wavlm && snapshot(e, 1, "L.gate", gate, 0, M, H, st)) return -1;
+    if (run_gemm(e, linear_op(xn, M, D, W.wqkv, 3 * D, epi_plain(W.bqkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * D)),
+                 st))
+      return -1;
+    if (snap && snapshot(e, 2, "L.qkv", qkv, 1, M, 3 * D, st)) return -1;
+    {
+      AttentionArgs a;
+      memset(&a, 0, sizeof(a));
+      a.qkv = qkv;
+      a.out = ctx;
+      a.B = B;
+      a.slot = slot;
+      a.H = H;
+      a.D = D;
+      a.lens = lens;
+      if (wavlm) {
+        a.gate = gate;
+        a.relbias = e->relbias.as<float>();
+        a.rel_stride = 2 * e->rel_R - 1;
+        a.rel_center = e->rel_R - 1;
+      }
+      e->launches++;
+      if (launch_attention(a, st, err)) return -1;
+    }
+    if (snap && snapshot(e, 3, "L.ctx", ctx, 1, M, D, st)) return -1;
+    if (pre_ln) {
+      if (run_gemm(e, linear_op(ctx, M, D, W.wo, D, epi_plain(W.bo, ACT_NONE, h, D, h, D, nullptr, 0)), st)) return -1;
+      if (snap && snapshot(e, 4, "L.h_attn", h, 0, M, D, st)) return -1;
+      LayerNormArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in_f32 = h;
+      a.rows = M;
+      a.D = D;
+      a.ld_in = D;
+      a.gamma = W.ln2_g;
+      a.beta = W.ln2_b;
+      a.eps = 1e-5f;
+      a.out_bf16 = xn;
+      a.ld_out16 = D;
+      e->launches++;
+      if (launch_layernorm(a, st, err)) return -1;
+      if (run_gemm(e, linear_op(xn, M, D, W.w1, F, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, F)), st))
+        return -1;
+      if (snap && snapshot(e, 5, "L.mid", mid, 1, M, F, st)) return -1;
+      EpiParams ep = epi_plain(W.b2, ACT_NONE, h, D, h, D, nullptr, 0);
+      const bool pool_here = (l < L - 1);  // hidden_states[l+1] = this layer's output (the last one is LN'd first)
+      if (pool_here && fused) {
+        ep.pool_part = part;
+        ep.pool_slot = slot;
+        ep.lens = lens;
+      }
+      if (run_gemm(e, linear_op(mid, M, F, W.w2, D, ep), st)) return -1;
+      if (snap && snapshot(e, 6, "L.h_out", h, 0, M, D, st)) return -1;
+      if (pool_here) {
+        if (fused) {
+          e->launches++;
+          if (launch_pool_finalize(part, B, slot, D, lens, pooled + (long long)(l + 1) * D, (long long)L1 * D, st, err))
+            return -1;
+        } else if (pool_into(e, h, B, slot, D, pooled, l + 1, L1, st)) {
+          return -1;
+        }
+      }
+    } else {
+      // post-LN (WavLM Base+)
+      if (run_gemm(e, linear_op(ctx, M, D, W.wo, D, epi_plain(W.bo, ACT_NONE, h, D, tmp, D, nullptr, 0)), st))
+        return -1;
+      LayerNormArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in_f32 = tmp;
+      a.rows = M;
+      a.D = D;
+      a.ld_in = D;
+      a.gamma = W.ln1_g;
+      a.beta = W.ln1_b;
+      a.eps = 1e-5f;
+      a.out_f32 = h;
+      a.ld_out32 = D;
+      a.out_bf16 = xn;
+      a.ld_out16 = D;
+      e->launches++;
+      if (launch_layernorm(a, st, err)) return -1;
+      if (snap && snapshot(e, 4, "L.h_attn", h, 0, M, D, st)) return -1;
+      if (run_gemm(e, linear_op(xn, M, D, W.w1, F, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, F)), st))
+        return -1;
+      if (snap && snapshot(e, 5, "L.mid", mid, 1, M, F, st)) return -1;
+      if (run_gemm(e, linear_op(mid, M, F, W.w2, D, epi_plain(W.b2, ACT_NONE, h, D, tmp, D, nullptr, 0)), st))
+        return -1;
+      memset(&a, 0, sizeof(a));
+      a.in_f32 = tmp;
+      a.rows = M;
+      a.D = D;
+      a.ld_in = D;
+      a.gamma = W.ln2_g;
+      a.beta = W.ln2_b;
+      a.eps = 1e-5f;
+      a.out_f32 = h;
+      a.ld_out32 = D;
+      a.out_bf16 = xn;
+      a.ld_out16 = D;
+      if (wavlm && l + 1 < L) {
+        const LayerW& Wn = e->layers[l + 1];
+        a.gate_out = gate;
+        a.gate_wa = Wn.gate_wa;
+        a.gate_wb = Wn.gate_wb;
+        a.gate_ba = Wn.gate_ba;
+        a.gate_bb = Wn.gate_bb;
+        a.gate_const = Wn.gate_const;
+        a.n_heads = H;
+      }
+      e->launches++;
+      if (launch_layernorm(a, st, err)) return -1;
+      if (snap && snapshot(e, 6, "L.h_out", h, 0, M, D, st)) return -1;
+      if (pool_into(e, h, B, slot, D, pooled, l + 1, L1, st)) return -1;
+    }
+  }
+  if (pre_ln) {
+    // hidden_states[L] = final LayerNorm of the last layer's output
+    LayerNormArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in_f32 = h;
+    a.rows = M;
+    a.D = D;
+    a.ld_in = D;
+    a.gamma = e->enc_ln_g;
+    a.beta = e->enc_ln_b;
+    a.eps = 1e-5f;
+    a.out_f32 = tmp;
+    a.ld_out32 = D;
+    e->launches++;
+    if (launch_layernorm(a, st, err)) return -1;
+    if (pool_into(e, tmp, B, slot, D, pooled, L, L1, st)) return -1;
+    reg_dbg(e, "last_hidden", tmp, 0, M, D);
+  } else {
+    reg_dbg(e, "last_hidden", h, 0, M, D);
+  }
+  return 0;
+}
+
+int upload_lengths(ssr_engine* e, const int32_t* n_samples, int B, const std::vector<int>& lens, cudaStream_t st) {
+  std::string& err = e->err;
+  if (e->nsamp_dev.ensure(sizeof(int) * B, st, err)) return -1;
+  if (e->lens_dev.ensure(sizeof(int) * B, st, err)) return -1;
+  CK(cudaMemcpyAsync(e->nsamp_dev.p, n_samples, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->lens_dev.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ WavLM forward
+int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int32_t* n_samples, int B,
+                  float* pooled, cudaStream_t st) {
+  std::string& err = e->err;
+  const ssr_model_desc& d = e->d;
+  const int D = d.hidden, H = d.heads, L1 = d.layers + 1;
+  static const int ks[7] = {10, 3, 3, 3, 3, 2, 2}, ss[7] = {5, 2, 2, 2, 2, 2, 2};
+  if (B <= 0) return 0;
+  int max_n = 0;
+  std::vector<int> lens(B);
+  for (int b = 0; b < B; ++b) {
+    if (n_samples[b] < 0 || n_samples[b] > audio_ld) {
+      err = "n_samples[" + std::to_string(b) + "] out of range";
+      return -1;
+    }
+    lens[b] = wavlm_frames(n_samples[b]);
+    if (lens[b] <= 0) {
+      err = "clip " + std::to_string(b) + " is too short for the WavLM feature encoder (needs >= 400 samples)";
+      return -1;
+    }
+    if (n_samples[b] > max_n) max_n = n_samples[b];
+  }
+  // Slotted flat layout: every clip owns S0 = roundup(max_n, 320) samples, hence S0/5, S0/10, ... S0/320 rows in the
+  // conv stack. Row t of clip b of layer i is flat row b*slot_i + t, so each strided conv is ONE 2-D GEMM view.
+  const long long S0 = ((long long)max_n + 319) / 320 * 320;
+  int slots[7];
+  {
+    long long s = S0;
+    for (int i = 0; i < 7; ++i) {
+      s /= ss[i];
+      slots[i] = (int)s;
+    }
+  }
+  const int slot = slots[6];
+  const long long Mll = (long long)B * slot;
+  if ((long long)B * slots[0] > 2000000000LL) {
+    err = "batch too large for 32-bit row indexing; split the batch";
+    return -1;
+  }
+  const int M = (int)Mll;
+  if (upload_lengths(e, n_samples, B, lens, st)) return -1;
+  if (build_relbias(e, slot, st, err)) return -1;
+
+  // workspace
+  for (int i = 0; i < 7; ++i)
+    if (e->conv[i].ensure(((size_t)B * slots[i] + 8) * 512 * 2, st, err)) return -1;
+  if (e->stats.ensure(sizeof(float) * 2 * B, st, err)) return -1;
+  if (d.feat_norm == SSR_FEAT_NORM_GROUP && e->gn_acc.ensure(sizeof(double) * 1024 * B, st, err)) return -1;
+  const int pslot = slot + 128;
+  if (e->feat_ln.ensure((size_t)M * 512 * 2, st, err)) return -1;
+  if (e->feat.ensure((size_t)M * D * 4, st, err)) return -1;
+  if (e->xp.ensure(((size_t)B * pslot + 256) * 1024 * 2, st, err)) return -1;
+  if (e->posconv.ensure((size_t)B * pslot * 1024 * 4, st, err)) return -1;
+  if (e->h.ensure((size_t)M * D * 4, st, err)) return -1;
+  if (e->tmp.ensure((size_t)M * D * 4, st, err)) return -1;
+  if (e->xn.ensure((size_t)M * D * 2, st, err)) return -1;
+  if (e->qkv.ensure((size_t)M * 3 * D * 2, st, err)) return -1;
+  if (e->ctx.ensure((size_t)M * D * 2, st, err)) return -1;
+  if (e->mid.ensure((size_t)M * d.ffn * 2, st, err)) return -1;
+  if (e->gate.ensure((size_t)M * H * 4, st, err)) return -1;
+  if (e->pool_part.ensure((size_t)ceil_div(M, 32) * 2 * D * 4, st, err)) return -1;
+
+  // 1. waveform normalisation + conv0 (+ norm + GELU)
+  {
+    Conv0Args a;
+    memset(&a, 0, sizeof(a));
+    a.audio = audio;
+    a.audio_ld = audio_ld;
+    a.n_samples = e->nsamp_dev.as<int>();
+    a.B = B;
+    a.do_normalize = d.do_normalize;
+    a.stats = e->stats.as<float>();
+    a.w = e->c0_w;
+    a.gamma = e->cln_g[0];
+    a.beta = e->cln_b[0];
+    a.mode = d.feat_norm == SSR_FEAT_NORM_LAYER ? 0 : 1;
+    a.gn_acc = e->gn_acc.as<double>();
+    a.out = e->conv[0].as<bf16>();
+    a.slot0 = slots[0];
+    e->launches += a.mode == 0 ? 2 : 4;
+    if (launch_wavlm_conv0(a, st, err)) return -1;
+    reg_dbg(e, "conv0", e->conv[0].p, 1, B, slots[0], 512);
+  }
+  // 2. conv layers 1..6 as implicit GEMMs over the channels-last signal
+  for (int i = 1; i < 7; ++i) {
+    const int Mi = B * slots[i];
+    GemmOp op;
+    op.A = e->conv[i - 1].as<bf16>();
+    op.lda = (long long)ss[i] * 512;
+    op.a_rows = Mi;
+    op.W = e->conv_w[i];
+    op.M = Mi;
+    op.N = 512;
+    op.K = ks[i] * 512;
+    op.a_mode = 0;
+    op.a_cols = 0;
+    const bool ln = d.feat_norm == SSR_FEAT_NORM_LAYER;
+    op.epi = epi_plain(nullptr, ln ? ACT_NONE : ACT_GELU, nullptr, 0, nullptr, 0, e->conv[i].as<bf16>(), 512);
+    if (run_gemm(e, op, st)) return -1;
+    if (ln) {
+      LayerNormArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in_bf16 = e->conv[i].as<bf16>();
+      a.rows = Mi;
+      a.D = 512;
+      a.ld_in = 512;
+      a.gamma = e->cln_g[i];
+      a.beta = e->cln_b[i];
+      a.eps = 1e-5f;
+      a.gelu = 1;
+      a.out_bf16 = e->conv[i].as<bf16>();
+      a.ld_out16 = 512;
+      e->launches++;
+      if (launch_layernorm(a, st, err)) return -1;
+    }
+    char nm[16];
+    snprintf(nm, sizeof nm, "conv%d", i);
+    reg_dbg(e, nm, e->conv[i].p, 1, B, slots[i], 512);
+  }
+  // 3. feature projection: LayerNorm(512) -> Linear(512 -> D)
+  {
+    LayerNormArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in_bf16 = e->conv[6].as<bf16>();
+    a.rows = M;
+    a.D = 512;
+    a.ld_in = 512;
+    a.gamma = e->fp_ln_g;
+    a.beta = e->fp_ln_b;
+    a.eps = 1e-5f;
+    a.out_bf16 = e->feat_ln.as<bf16>();
+    a.ld_out16 = 512;
+    e->launches++;
+    if (launch_layernorm(a, st, err)) return -1;
+    if (run_gemm(e,
+                 linear_op(e->feat_ln.as<bf16>(), M, 512, e->fp_w, D,
+                           epi_plain(e->fp_b, ACT_NONE, nullptr, 0, e->feat.as<float>(), D, nullptr, 0)),
+                 st))
+      return -1;
+    reg_dbg(e, "feat", e->feat.p, 0, B, slot, D);
+  }
+  // 4. positional conv embedding (grouped conv k=128 as 16 block-diagonal GEMMs with K = 128 taps x 64 channels)
+  {
+    e->launches++;
+    if (launch_posconv_pack(e->feat.as<float>(), B, slot, D, e->lens_dev.as<int>(), e->xp.as<bf16>(), pslot, st, err))
+      return -1;
+    GemmOp op;
+    op.A = e->xp.as<bf16>();
+    op.lda = 1024;
+    op.a_rows = (long long)B * pslot + 128;
+    op.W = e->pos_w;
+    op.M = B * pslot;
+    op.N = 1024;
+    op.K = 8192;
+    op.a_mode = 1;
+    op.a_cols = 1024;
+    op.epi = epi_plain(nullptr, ACT_NONE, nullptr, 0, e->posconv.as<float>(), 1024, nullptr, 0);
+    if (run_gemm(e, op, st)) return -1;
+    const bool stable = d.stable_ln != 0;
+    float* dst = stable ? e->h.as<float>() : e->tmp.as<float>();
+    e->launches++;
+    if (launch_posconv_finish(e->posconv.as<float>(), pslot, e->pos_b, e->feat.as<float>(), B, slot, D,
+                              e->lens_dev.as<int>(), dst, st, err))
+      return -1;
+    if (!stable) {
+      // Base+: encoder.layer_norm right after the positional add; its output is hidden_states[0]
+      LayerNormArgs a;
+      memset(&a, 0, sizeof(a));
+      a.in_f32 = dst;
+      a.rows = M;
+      a.D = D;
+      a.ld_in = D;
+      a.gamma = e->enc_ln_g;
+      a.beta = e->enc_ln_b;
+      a.eps = 1e-5f;
+      a.out_f32 = e->h.as<float>();
+      a.ld_out32 = D;
+      a.out_bf16 = e->xn.as<bf16>();
+      a.ld_out16 = D;
+      const LayerW& W0 = e->layers[0];
+      a.gate_out = e->gate.as<float>();
+      a.gate_wa = W0.gate_wa;
+      a.gate_wb = W0.gate_wb;
+      a.gate_ba = W0.gate_ba;
+      a.gate_bb = W0.gate_bb;
+      a.gate_const = W0.gate_const;
+      a.n_heads = H;
+      e->launches++;
+      if (launch_layernorm(a, st, err)) return -1;
+    }
+    if (pool_into(e, e->h.as<float>(), B, slot, D, pooled, 0, L1, st)) return -1;
+    if (e->opt_snapshot_layer >= 0 && snapshot(e, 7, "hs0", e->h.p, 0, M, D, st)) return -1;
+  }
+  // 5. transformer
+  return run_layers(e, B, slot, d.stable_ln != 0, true, pooled, st);
+}
+
+// ------------------------------------------------------------------------------------------------ Whisper forward
+int whisper_logmel(ssr_engine* e, const float* audio, int64_t audio_ld, const int32_t* n_samples, int B,
+                   float* mel_out, bool want_conv_in, cudaStream_t st) {
+  std::string& err = e->err;
+  int max_n = 0;
+  std::vector<int> lens(B, 1500);
+  for (int b = 0; b < B; ++b) {
+    if (n_samples[b] < 0 || n_samples[b] > audio_ld) {
+      err = "n_samples[" + std::to_string(b) + "] out of range";
+      return -1;
+    }
+    if (n_samples[b] > max_n) max_n = n_samples[b];
+  }
+  if (upload_lengths(e, n_samples, B, lens, st)) return -1;
+  if (e->logspec.ensure((size_t)B * 3000 * 80 * 4, st, err)) return -1;
+  if (e->gmax.ensure((size_t)B * 4, st, err)) return -1;
+  if (want_conv_in && e->conv_in.ensure(((size_t)B * 3002 + 8) * 80 * 2, st, err)) return -1;
+  LogMelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.audio = audio;
+  a.audio_ld = audio_ld;
+  a.n_samples = e->nsamp_dev.as<int>();
+  a.B = B;
+  a.max_samples = max_n;
+  a.twiddle = e->twiddle;
+  a.melw = e->melw;
+  a.mel_lo = e->mel_lo;
+  a.mel_hi = e->mel_hi;
+  a.logspec = e->logspec.as<float>();
+  a.gmax = e->gmax.as<unsigned int>();
+  a.mel_out = mel_out;
+  a.conv_in = want_conv_in ? e->conv_in.as<bf16>() : nullptr;
+  e->launches += 3;
+  return launch_logmel(a, st, err);
+}
+
+int whisper_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int32_t* n_samples, int B,
+                    float* pooled, cudaStream_t st) {
+  std::string& err = e->err;
+  const ssr_model_desc& d = e->d;
+  const int D = d.hidden, L1 = d.layers + 1;
+  if (B <= 0) return 0;
+  if ((long long)B * 3002 > 2000000000LL / 1) {
+    err = "batch too large";
+    return -1;
+  }
+  if (whisper_logmel(e, audio, audio_ld, n_samples, B, nullptr, true, st)) return -1;
+  const int M = B * 1500;
+  if (e->c1.ensure(((size_t)B * 3002 + 8) * D * 2, st, err)) return -1;
+  if (e->h.ensure((size_t)M * D * 4, st, err)) return -1;
+  if (e->tmp.ensure((size_t)M * D * 4, st, err)) return -1;
+  if (e->xn.ensure((size_t)M * D * 2, st, err)) return -1;
+  if (e->qkv.ensure((size_t)M * 3 * D * 2, st, err)) return -1;
+  if (e->ctx.ensure((size_t)M * D * 2, st, err)) return -1;
+  if (e->mid.ensure((size_t)M * d.ffn * 2, st, err)) return -1;
+  if (e->pool_part.ensure((size_t)ceil_div(B * 1501, 32) * 2 * D * 4, st, err)) return -1;
+  reg_dbg(e, "conv_in", e->conv_in.p, 1, B, 3002, 80);
+  // conv1: k=3, pad=1 over the zero-padded channels-last mel; GELU; written into conv2's padded input
+  {
+    GemmOp op;
+    op.A = e->conv_in.as<bf16>();
+    op.lda = 80;
+    op.a_rows = (long long)B * 3002;
+    op.W = e->wc1;
+    op.M = B * 3002;
+    op.N = D;
+    op.K = 240;
+    op.a_mode = 0;
+    op.a_cols = 0;
+    op.epi = epi_plain(e->bc1, ACT_GELU, nullptr, 0, nullptr, 0, e->c1.as<bf16>(), D);
+    op.epi.in_slot = 3002;
+    op.epi.out_slot = 3002;
+    op.epi.valid = 3000;
+    op.epi.out_off = 1;
+    if (run_gemm(e, op, st)) return -1;
+    reg_dbg(e, "c1", e->c1.p, 1, B, 3002, D);
+  }
+  // conv2: k=3, stride 2, pad=1; GELU; + embed_positions; this is hidden_states[0]
+  {
+    GemmOp op;
+    op.A = e->c1.as<bf16>();
+    op.lda = 2LL * D;
+    op.a_rows = (long long)B * 1501;
+    op.W = e->wc2;
+    op.M = B * 1501;
+    op.N = D;
+    op.K = 3 * D;
+    op.a_mode = 0;
+    op.a_cols = 0;
+    op.epi = epi_plain(e->bc2, ACT_GELU, e->pos_emb, D, e->h.as<float>(), D, nullptr, 0);
+    op.epi.in_slot = 1501;
+    op.epi.out_slot = 1500;
+    op.epi.valid = 1500;
+    op.epi.out_off = 0;
+    op.epi.resid_by_t = 1;
+    const bool fused = e->opt_fused_pool != 0;
+    if (fused) op.epi.pool_part = e->pool_part.as<float>();
+    if (run_gemm(e, op, st)) return -1;
+    if (fused) {
+      e->launches++;
+      if (launch_pool_finalize(e->pool_part.as<float>(), B, 1501, D, e->lens_dev.as<int>(), pooled,
+                               (long long)L1 * D, st, err))
+        return -1;
+    } else if (pool_into(e, e->h.as<float>(), B, 1500, D, pooled, 0, L1, st)) {
+      return -1;
+    }
+    if (e->opt_snapshot_layer >= 0 && snapshot(e, 7, "hs0", e->h.p, 0, M, D, st)) return -1;
+  }
+  return run_layers(e, B, 1500, true, false, pooled, st);
+}
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+void copy_err(const std::string& s, char* err, int32_t err_len) {
+  if (err && err_len > 0) {
+    snprintf(err, (size_t)err_len, "%s", s.c_str());
+  }
+}
+
+}  // namespace
+
+// ================================================================================================== C ABI
+extern "C" {
+
+int ssr_create(const ssr_model_desc* desc, const ssr_weight* weights, int32_t n_weights, int32_t cuda_device,
+               ssr_engine** out) {
+  if (!desc || !out || (!weights && n_weights > 0)) {
+    g_create_error = "ssr_create: null argument";
+    return -1;
+  }
+  *out = nullptr;
+  std::string err;
+  cudaError_t ce = cudaSetDevice(cuda_device);
+  if (ce != cudaSuccess) {
+    g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(ce);
+    return -2;
+  }
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, cuda_device);
+  if (ce != cudaSuccess) {
+    g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(ce);
+    return -2;
+  }
+  if (prop.major != 10) {
+    g_create_error = "ssr_b200 kernels are built for sm_100a (Blackwell B200) only; found compute capability " +
+                     std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return -3;
+  }
+  std::unique_ptr<ssr_engine> e(new ssr_engine());
+  e->d = *desc;
+  e->device = cuda_device;
+  e->num_sms = prop.multiProcessorCount;
+  WeightMap wm;
+  for (int i = 0; i < n_weights; ++i) {
+    if (!weights[i].name || !weights[i].data) {
+      g_create_error = "ssr_create: weight entry with null name or data";
+      return -1;
+    }
+    wm.m[weights[i].name] = &weights[i];
+  }
+  int rc;
+  if (desc->family == SSR_WAVLM)
+    rc = create_wavlm(e.get(), wm, err);
+  else if (desc->family == SSR_WHISPER_ENC)
+    rc = create_whisper(e.get(), wm, err);
+  else {
+    g_create_error = "ssr_create: unknown model family";
+    return -1;
+  }
+  if (rc) {
+    g_create_error = !wm.err.empty() ? wm.err : (err.empty() ? "ssr_create failed" : err);
+    return -4;
+  }
+  *out = e.release();
+  return 0;
+}
+
+void ssr_destroy(ssr_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+const char* ssr_last_error(const ssr_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
+  if (!e || !key) return -1;
+  const std::string k(key);
+  if (k == "simt_gemm")
+    e->opt_simt = value;
+  else if (k == "fused_pool")
+    e->opt_fused_pool = value;
+  else if (k == "snapshot_layer")
+    e->opt_snapshot_layer = value;
+  else {
+    e->err = "unknown option '" + k + "'";
+    return -1;
+  }
+  return 0;
+}
+
+int ssr_wavlm_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
+                     float* pooled_dev, void* cuda_stream) {
+  if (!e) return -1;
+  if (e->d.family != SSR_WAVLM) {
+    e->err = "engine is not a WavLM engine";
+    return -1;
+  }
+  if (!audio_dev || !n_samples || !pooled_dev || B < 0) {
+    e->err = "ssr_wavlm_pooled: null argument";
+    return -1;
+  }
+  cudaSetDevice(e->device);
+  return wavlm_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, as_stream(cuda_stream));
+}
+
+int ssr_whisper_enc_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples,
+                           int32_t B, float* pooled_dev, void* cuda_stream) {
+  if (!e) return -1;
+  if (e->d.family != SSR_WHISPER_ENC) {
+    e->err = "engine is not a Whisper engine";
+    return -1;
+  }
+  if (!audio_dev || !n_samples || !pooled_dev || B < 0) {
+    e->err = "ssr_whisper_enc_pooled: null argument";
+    return -1;
+  }
+  cudaSetDevice(e->device);
+  return whisper_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, as_stream(cuda_stream));
+}
+
+int ssr_logmel(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
+               float* mel_dev, void* cuda_stream) {
+  if (!e) return -1;
+  if (e->d.family != SSR_WHISPER_ENC) {
+    e->err = "engine is not a Whisper engine";
+    return -1;
+  }
+  if (!audio_dev || !n_samples || !mel_dev || B < 0) {
+    e->err = "ssr_logmel: null argument";
+    return -1;
+  }
+  cudaSetDevice(e->device);
+  if (B == 0) return 0;
+  return whisper_logmel(e, audio_dev, audio_ld, n_samples, B, mel_dev, false, as_stream(cuda_stream));
+}
+
+static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                    int32_t B, float* pooled_host) {
+  std::string& err = e->err;
+  if (!audio_host || !n_samples || !pooled_host || B < 0) {
+    err = "host entry point: null argument";
+    return -1;
+  }
+  if (B == 0) return 0;
+  cudaSetDevice(e->device);
+  cudaStream_t st = nullptr;
+  const size_t in_bytes = (size_t)B * audio_ld * 4;
+  const size_t out_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
+  if (e->audio_stage.ensure(in_bytes, st, err)) return -1;
+  if (e->pooled_stage.ensure(out_bytes, st, err)) return -1;
+  CK(cudaMemcpyAsync(e->audio_stage.p, audio_host, in_bytes, cudaMemcpyHostToDevice, st));
+  int rc = wavlm ? wavlm_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B, e->pooled_stage.as<float>(), st)
+                 : whisper_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B,
+                                   e->pooled_stage.as<float>(), st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(pooled_host, e->pooled_stage.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ssr_wavlm_pooled_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                          int32_t B, float* pooled_host) {
+  if (!e) return -1;
+  if (e->d.family != SSR_WAVLM) {
+    e->err = "engine is not a WavLM engine";
+    return -1;
+  }
+  return run_host(e, true, audio_host, audio_ld, n_samples, B, pooled_host);
+}
+
+int ssr_whisper_enc_pooled_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                                int32_t B, float* pooled_host) {
+  if (!e) return -1;
+  if (e->d.family != SSR_WHISPER_ENC) {
+    e->err = "engine is not a Whisper engine";
+    return -1;
+  }
+  return run_host(e, false, audio_host, audio_ld, n_samples, B, pooled_host);
+}
+
+int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples) {
+  if (!e) return -1;
+  return e->d.family == SSR_WAVLM ? wavlm_frames(n_samples) : 1500;
+}
+
+int64_t ssr_launch_count(const ssr_engine* e) { return e ? e->launches : -1; }
+
+int ssr_gemm_bf16(int32_t cuda_device, const void* A, int64_t lda, int64_t a_rows, const void* W, int32_t M,
+                  int32_t N, int32_t K, const float* bias, int32_t act, const float* resid, float* out_f32,
+                  void* out_bf16, int32_t simt, void* cuda_stream, char* errbuf, int32_t err_len) {
+  std::string err;
+  cudaSetDevice(cuda_device);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_device);
+  GemmOp op;
+  op.A = reinterpret_cast<const bf16*>(A);
+  op.lda = lda;
+  op.a_rows = a_rows;
+  op.W = reinterpret_cast<const bf16*>(W);
+  op.M = M;
+  op.N = N;
+  op.K = K;
+  op.a_mode = 0;
+  op.a_cols = 0;
+  op.epi = epi_plain(bias, act, resid, N, out_f32, N, reinterpret_cast<bf16*>(out_bf16), N);
+  int rc = launch_gemm(op, as_stream(cuda_stream), simt != 0, sms, err);
+  if (rc) copy_err(err, errbuf, err_len);
+  return rc;
+}
+
+int ssr_gemm_bf16_pool(int32_t cuda_device, const void* A, int64_t lda, const void* W, int32_t M, int32_t N, int32_t K,
+                       const float* bias, int32_t act, const float* resid, float* out_f32, int32_t slot,
+                       const int32_t* lens_dev, int32_t B, float* part_dev, float* pooled_dev, int64_t pooled_ld,
+                       int32_t simt, void* cuda_stream, char* errbuf, int32_t err_len) {
+  std::string err;
+  cudaSetDevice(cuda_device);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cuda_device);
+  GemmOp op;
+  op.A = reinterpret_cast<const bf16*>(A);
+  op.lda = lda;
+  op.a_rows = M;
+  op.W = reinterpret_cast<const bf16*>(W);
+  op.M = M;
+  op.N = N;
+  op.K = K;
+  op.a_mode = 0;
+  op.a_cols = 0;
+  op.epi = epi_plain(bias, act, resid, N, out_f32, N, nullptr, 0);
+  op.epi.pool_part = part_dev;
+  op.epi.pool_slot = slot;
+  op.epi.lens = lens_dev;
+  int rc = launch_gemm(op, as_stream(cuda_stream), simt != 0, sms, err);
+  if (!rc) rc = launch_pool_finalize(part_dev, B, slot, N, lens_dev, pooled_dev, pooled_ld, as_stream(cuda_stream), err);
+  if (rc) copy_err(err, errbuf, err_len);
+  return rc;
+}
+
+int ssr_layernorm(const float* in_f32, const void* in_bf16, int64_t rows, int32_t D, const float* gamma,
+                  const float* beta, int32_t gelu, float* out_f32, void* out_bf16, void* cuda_stream, char* errbuf,
+                  int32_t err_len) {
+  std::string err;
+  LayerNormArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in_f32 = in_f32;
+  a.in_bf16 = reinterpret_cast<const bf16*>(in_bf16);
+  a.rows = rows;
+  a.D = D;
+  a.ld_in = D;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.eps = 1e-5f;
+  a.gelu = gelu;
+  a.out_f32 = out_f32;
+  a.ld_out32 = D;
+  a.out_bf16 = reinterpret_cast<bf16*>(out_bf16);
+  a.ld_out16 = D;
+  int rc = launch_layernorm(a, as_stream(cuda_stream), err);
+  if (rc) copy_err(err, errbuf, err_len);
+  return rc;
+}
+
+int ssr_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t slot, int32_t H, const int32_t* lens_dev,
+                  const float* gate, const float* relbias, int32_t rel_stride, int32_t rel_center, void* cuda_stream,
+                  char* errbuf, int32_t err_len) {
+  std::string err;
+  AttentionArgs a;
+  memset(&a, 0, sizeof(a));
+  a.qkv = reinterpret_cast<const bf16*>(qkv_bf16);
+  a.out = reinterpret_cast<bf16*>(out_bf16);
+  a.B = B;
+  a.slot = slot;
+  a.H = H;
+  a.D = H * 64;
+  a.lens = lens_dev;
+  a.gate = gate;
+  a.relbias = relbias;
+  a.rel_stride = rel_stride;
+  a.rel_center = rel_center;
+  int rc = launch_attention(a, as_stream(cuda_stream), err);
+  if (rc) copy_err(err, errbuf, err_len);
+  return rc;
+}
+
+int ssr_pool_mean(const float* x, int32_t B, int32_t slot, int32_t D, const int32_t* lens_dev, float* pooled,
+                  int64_t pooled_ld, void* cuda_stream, char* errbuf, int32_t err_len) {
+  std::string err;
+  int rc = launch_pool_mean(x, B, slot, D, lens_dev, pooled, pooled_ld, as_stream(cuda_stream), err);
+  if (rc) copy_err(err, errbuf, err_len);
+  return rc;
+}
+
+int64_t ssr_debug_fetch(ssr_engine* e, const char* name, void* dst_host, int64_t dst_bytes, int64_t* dims,
+                        int32_t* dtype) {
+  if (!e || !name) return -1;
+  auto it = e->dbg.find(name);
+  if (it == e->dbg.end()) {
+    e->err = std::string("no debug buffer named '") + name + "'";
+    return -1;
+  }
+  const DbgBuf& b = it->second;
+  if (dims) memcpy(dims, b.dims, sizeof(b.dims));
+  if (dtype) *dtype = b.dtype;
+  if (!dst_host) return b.bytes;
+  if (dst_bytes < b.bytes) {
+    e->err = "debug fetch: destination too small";
+    return -2;
+  }
+  cudaSetDevice(e->device);
+  cudaError_t ce = cudaDeviceSynchronize();
+  if (ce == cudaSuccess) ce = cudaMemcpy(dst_host, b.p, (size_t)b.bytes, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) {
+    e->err = std::string("debug fetch: ") + cudaGetErrorString(ce);
+    return -3;
+  }
+  return b.bytes;
+}
+
+}  // extern "C"

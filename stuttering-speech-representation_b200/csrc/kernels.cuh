@@ -1,0 +1,90 @@
+// Launcher declarations for the non-GEMM kernels (internal).
+#pragma once
+#include "common.cuh"
+
+namespace ssr {
+
+struct LayerNormArgs {
+  const float* in_f32;  // exactly one of in_f32 / in_bf16
+  const bf16* in_bf16;
+  long long rows;
+  int D;
+  long long ld_in;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int gelu;
+  float* out_f32;
+  long long ld_out32;
+  bf16* out_bf16;
+  long long ld_out16;
+  // optional WavLM gate (needs head_dim 64)
+  float* gate_out;  // [rows, n_heads]
+  const float* gate_wa;
+  const float* gate_wb;
+  float gate_ba, gate_bb;
+  const float* gate_const;  // [n_heads]
+  int n_heads;
+};
+int launch_layernorm(const LayerNormArgs& a, cudaStream_t st, std::string& err);
+
+int launch_pool_mean(const float* x, int B, int slot, int D, const int* lens, float* out, long long out_stride,
+                     cudaStream_t st, std::string& err);
+int launch_pool_finalize(const float* part, int B, int slot, int D, const int* lens, float* out, long long out_stride,
+                         cudaStream_t st, std::string& err);
+int launch_posconv_pack(const float* x, int B, int slot, int D, const int* lens, bf16* xp, int pslot, cudaStream_t st,
+                        std::string& err);
+int launch_posconv_finish(const float* conv, int pslot, const float* bias, const float* x, int B, int slot, int D,
+                          const int* lens, float* h, cudaStream_t st, std::string& err);
+
+// Multi-head self-attention over fused qkv [B*slot, 3*D] (bf16; q already scaled), head_dim 64.
+// Keys j >= lens[b] are masked. If gate != nullptr the WavLM gated relative-position bias is added:
+//   score[i, j] += gate[b*slot + i, h] * relbias[h * rel_stride + (j - i) + rel_center]
+struct AttentionArgs {
+  const bf16* qkv;
+  bf16* out;  // [B*slot, D]
+  int B, slot, H, D;
+  const int* lens;
+  const float* gate;
+  const float* relbias;
+  int rel_stride, rel_center;
+};
+int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);
+
+// WavLM waveform statistics + first conv layer (C_in = 1, k = 10, stride 5) fused with its normalisation + GELU.
+struct Conv0Args {
+  const float* audio;  // [B, audio_ld]
+  long long audio_ld;
+  const int* n_samples;  // [B] device
+  int B;
+  int do_normalize;  // Wav2Vec2FeatureExtractor zero-mean / unit-variance
+  float* stats;      // [B, 2] mean, rstd (scratch)
+  const float* w;    // [512, 10]
+  const float* gamma;
+  const float* beta;  // [512]
+  int mode;           // 0: LayerNorm over channels (Large); 1: GroupNorm over time (Base+)
+  double* gn_acc;     // [B, 512, 2] scratch for mode 1
+  bf16* out;          // [B, slot0, 512]
+  int slot0;          // rows per clip in out
+};
+int launch_wavlm_conv0(const Conv0Args& a, cudaStream_t st, std::string& err);
+
+// Whisper log-mel front end.
+struct LogMelArgs {
+  const float* audio;
+  long long audio_ld;
+  const int* n_samples;  // device [B]
+  int B;
+  int max_samples;       // max over the batch (host-known bound on live frames)
+  const float* twiddle;  // [400, 416] fp32 : col 2f = cos, 2f+1 = -sin (f < 201), zero padded
+  const float* melw;     // [80, 201] fp32 dense filterbank
+  const int* mel_lo;     // [80] first non-zero bin
+  const int* mel_hi;     // [80] last non-zero bin
+  float* logspec;        // scratch [B, 3000, 80] fp32 (log10 mel, un-normalised)
+  unsigned int* gmax;    // scratch [B] ordered-uint encoding of the per-clip max
+  float* mel_out;        // optional [B, 80, 3000] fp32 (HF layout)
+  bf16* conv_in;         // optional [B, 3002, 80] bf16 channels-last with one zero row each side
+};
+int launch_logmel(const LogMelArgs& a, cudaStream_t st, std::string& err);
+
+}  // namespace ssr

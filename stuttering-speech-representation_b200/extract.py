@@ -1,0 +1,182 @@
+"""Drop-in replacements for the reference's four per-clip extraction functions (same names, argument order,
+return type and error behaviour), backed by the CUDA engine.
+
+    extract_wavlm_embeddings               REF/WavLM_embeddings.py:267-341
+    extract_embeddings_from_audio_wavlm    REF/model_training_1.py:235-266  (== REF/model_training_01.py:214-245)
+    extract_whisper_embeddings_fixed       REF/whisper_embeddings_large.py:234-299  (encoder outputs)
+    extract_embeddings_from_audio_whisper  REF/model_training_1.py:268-316           (encoder outputs)
+
+Contract kept from the reference: returns `{layer_name: float32 ndarray of shape (D,)}` in the iteration order of
+the index list; an out-of-range index is skipped with a warning; any failure is logged and `None` is returned —
+nothing is raised to the caller (REF/WavLM_embeddings.py:329-341).  The `model` / `feature_extractor` arguments are
+the HF objects the reference scripts already hold; an engine is built from them once and cached per model object.
+The `device` argument is accepted for signature compatibility: the engine always runs on CUDA.
+
+`decoder_layer_*` entries are OUT OF SCOPE of this path: they are skipped with a warning.
+
+Batched entry points (`*_batch`) are the efficient way in: the reference's per-clip loop costs one H2D / D2H
+round trip per clip.
+"""
+from __future__ import annotations
+
+import logging
+import wave
+import weakref
+from typing import Sequence
+
+import numpy as np
+
+from .engine import WavLMEngine, WhisperEncoderEngine
+
+logger = logging.getLogger("ssr_b200")
+
+_ENGINES: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def get_engine(model, feature_extractor=None, device=0):
+    """Engine for an HF model object, built on first use from model.state_dict() and cached on the object."""
+    key = (type(feature_extractor).__name__, bool(getattr(feature_extractor, "do_normalize", False)))
+    per_model = _ENGINES.setdefault(model, {})
+    eng = per_model.get(key)
+    if eng is None:
+        dev = _device_index(device)
+        name = type(model).__name__.lower()
+        if "wavlm" in name:
+            eng = WavLMEngine.from_hf(model, feature_extractor, dev)
+        elif "whisper" in name:
+            eng = WhisperEncoderEngine.from_hf(model, feature_extractor, dev)
+        else:
+            raise TypeError(f"unsupported model type {type(model).__name__}")
+        per_model[key] = eng
+    return eng
+
+
+def _device_index(device) -> int:
+    if isinstance(device, int):
+        return device
+    idx = getattr(device, "index", None)
+    if idx is not None:
+        return int(idx)
+    s = str(device)
+    return int(s.split(":")[1]) if ":" in s else 0
+
+
+def load_audio(file_path, target_sr=16000, max_length=None):
+    """Minimal stand-in for the reference's torchaudio loader (REF/WavLM_embeddings.py:87-125; out of scope of the
+    hot path): PCM WAV via the standard library, mono mix-down, optional trim. Returns None on failure."""
+    try:
+        with wave.open(str(file_path), "rb") as w:
+            sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n)
+        if width == 2:
+            x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif width == 4:
+            x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif width == 1:
+            x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        else:
+            raise ValueError(f"unsupported sample width {width}")
+        if nch > 1:
+            x = x.reshape(-1, nch).mean(axis=1)
+        if sr != target_sr:
+            raise ValueError(f"sample rate {sr} != {target_sr}; resampling is outside the hot path")
+        if max_length is not None:
+            x = x[: int(max_length * target_sr)]
+        return np.ascontiguousarray(x, dtype=np.float32)
+    except Exception as e:  # noqa: BLE001 - reference behaviour: log and return None
+        logger.error(f"Error loading {file_path}: {e}")
+        return None
+
+
+def pooled_to_layer_dict(pooled_clip: np.ndarray, indices: Sequence[int], prefix: str) -> dict:
+    """pooled_clip: [L+1, D]. Mirrors the reference's selection loop (REF/WavLM_embeddings.py:315-325)."""
+    out = {}
+    n = pooled_clip.shape[0]
+    for idx in indices:
+        if idx < n:
+            out[f"{prefix}{idx}"] = np.ascontiguousarray(pooled_clip[idx], dtype=np.float32).flatten()
+        else:
+            logger.warning(f"Layer {idx} is out of range (max: {n - 1})")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- WavLM
+def extract_embeddings_from_audio_wavlm(audio_array, model, feature_extractor, device, layer_indices):
+    try:
+        eng = get_engine(model, feature_extractor, device)
+        pooled = eng.pooled([audio_array])
+        return pooled_to_layer_dict(pooled[0], layer_indices, "layer_")
+    except Exception as e:  # noqa: BLE001
+        logger.error(f"Error extracting WavLM embeddings: {e}")
+        return None
+
+
+def extract_wavlm_embeddings(audio_file, model, feature_extractor, device, layer_indices, max_length=None,
+                             sample_rate=16000):
+    audio_array = load_audio(audio_file, target_sr=sample_rate, max_length=max_length)
+    if audio_array is None:
+        return None
+    if audio_array.shape[0] > 500000:
+        logger.warning(f"Very long input ({audio_array.shape[0]} samples, ~{audio_array.shape[0] / sample_rate:.2f}s)."
+                       " This may cause memory issues.")
+    return extract_embeddings_from_audio_wavlm(audio_array, model, feature_extractor, device, layer_indices)
+
+
+def extract_wavlm_embeddings_batch(audio_arrays, model, feature_extractor, device, layer_indices):
+    """Batched form: list of clips -> list of dicts (None for the whole batch on failure)."""
+    try:
+        eng = get_engine(model, feature_extractor, device)
+        pooled = eng.pooled(list(audio_arrays))
+        return [pooled_to_layer_dict(p, layer_indices, "layer_") for p in pooled]
+    except Exception as e:  # noqa: BLE001
+        logger.error(f"Error extracting WavLM embeddings: {e}")
+        return None
+
+
+# ---------------------------------------------------------------------------------------------- Whisper
+def _whisper_dict(pooled_clip, encoder_indices, decoder_names):
+    out = pooled_to_layer_dict(pooled_clip, encoder_indices, "encoder_layer_")
+    for nm in decoder_names:
+        logger.warning(f"{nm}: the Whisper decoder pass is outside this engine's scope; entry skipped")
+    return out
+
+
+def extract_embeddings_from_audio_whisper(audio_array, model, processor, device, layer_names):
+    try:
+        eng = get_engine(model, processor, device)
+        pooled = eng.pooled([audio_array])[0]
+        out = {}
+        for layer_name in layer_names:
+            if layer_name.startswith("encoder_layer_"):
+                idx = int(layer_name.split("_")[-1])
+                if idx < pooled.shape[0]:
+                    out[layer_name] = np.ascontiguousarray(pooled[idx], dtype=np.float32).flatten()
+            elif layer_name.startswith("decoder_layer_"):
+                logger.warning(f"{layer_name}: the Whisper decoder pass is outside this engine's scope; skipped")
+        return out
+    except Exception as e:  # noqa: BLE001
+        logger.error(f"Error extracting Whisper embeddings: {e}")
+        return None
+
+
+def extract_whisper_embeddings_fixed(audio_file, model, processor, device, encoder_indices, decoder_indices):
+    audio_array = load_audio(audio_file)
+    if audio_array is None:
+        return None
+    try:
+        eng = get_engine(model, processor, device)
+        pooled = eng.pooled([audio_array])[0]
+        return _whisper_dict(pooled, encoder_indices, [f"decoder_layer_{i}" for i in decoder_indices])
+    except Exception as e:  # noqa: BLE001
+        logger.error(f"Error extracting Whisper embeddings: {e}")
+        return None
+
+
+def extract_whisper_embeddings_batch(audio_arrays, model, processor, device, encoder_indices):
+    try:
+        eng = get_engine(model, processor, device)
+        pooled = eng.pooled(list(audio_arrays))
+        return [pooled_to_layer_dict(p, encoder_indices, "encoder_layer_") for p in pooled]
+    except Exception as e:  # noqa: BLE001
+        logger.error(f"Error extracting Whisper embeddings: {e}")
+        return None
