@@ -63,7 +63,8 @@ void ssr_destroy(ssr_engine* e);
 /* e == NULL returns the message of the last failed ssr_create on this thread's process. */
 const char* ssr_last_error(const ssr_engine* e);
 
-/* Options: "simt_gemm" (bring-up cross-check GEMM), "fused_pool" (default 1), "snapshot_layer" (-1 = off).
+/* Options: "simt_gemm" (bring-up cross-check GEMM), "fused_pool" (default 1), "snapshot_layer" (-1 = off),
+ * "profile" (1 = bracket every kernel launch with CUDA events on the launching stream; read with ssr_profile_fetch).
  * Returns 0, or -1 for an unknown key. */
 int ssr_set_option(ssr_engine* e, const char* key, int32_t value);
 
@@ -90,7 +91,10 @@ int ssr_whisper_enc_pooled_host(ssr_engine* e, const float* audio_host, int64_t 
 int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples);
 /* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t ssr_launch_count(const ssr_engine* e);
-/* Device-event time (ms) of the most recent GEMM launches is not tracked here; timing is the caller's job. */
+/* With option "profile" = 1: synchronises, then returns a JSON object
+ *   {"<kernel group>": {"launches": n, "ms": device-event milliseconds, "flops": algorithmic FLOPs}, ...}
+ * aggregated over every launch since the previous fetch (string owned by the engine, valid until the next call). */
+const char* ssr_profile_fetch(ssr_engine* e);
 
 /* ---- stage-level entry points (kernel parity tests; all pointers are device pointers) ------------------------ */
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) + resid ; A row r starts at A + r*lda (bf16), rows >= a_rows read zero.

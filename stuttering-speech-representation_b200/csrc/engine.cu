@@ -76,6 +76,12 @@ struct DbgBuf {
   int32_t dtype;
 };
 
+struct ProfEntry {
+  std::string name;
+  cudaEvent_t a, b;
+  double flops;
+};
+
 struct LayerW {
   bf16 *wqkv, *wo, *w1, *w2;
   float *bqkv, *bo, *b1, *b2;
@@ -93,7 +99,9 @@ struct ssr_engine {
   std::string err;
   int64_t launches = 0;
   // options
-  int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1;
+  int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1, opt_profile = 0;
+  std::vector<ProfEntry> prof;
+  std::string prof_json;
 
   // ---- weights (device) ----
   std::vector<void*> owned;  // every cudaMalloc'd weight block
@@ -350,8 +358,8 @@ int create_wavlm(ssr_engine* e, WeightMap& w, std::string& err) {
 int create_whisper(ssr_engine* e, WeightMap& w, std::string& err) {
   const ssr_model_desc& d = e->d;
   const int D = d.hidden, F = d.ffn, H = d.heads, L = d.layers, NM = d.n_mels;
-  if (D != H * 64 || D % 256 != 0) {
-    err = "Whisper: head_dim must be 64 and d_model a multiple of 256";
+  if (D != H * 64 || D % 128 != 0 || D > 1280) {
+    err = "Whisper: head_dim must be 64 and d_model one of 256, 384, 512, 768, 1024, 1280";
     return -1;
   }
   if (NM != 80) {
@@ -441,9 +449,43 @@ EpiParams epi_plain(const float* bias, int act, const float* resid, int ldr, flo
   return ep;
 }
 
-int run_gemm(ssr_engine* e, const GemmOp& op, cudaStream_t st) {
+// Per-launch CUDA-event timing (option "profile"): events go on the launching stream around each kernel group.
+struct ProfScope {
+  ssr_engine* e;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(ssr_engine* e_, cudaStream_t st_, const char* name, double flops = 0.0) : e(e_), st(st_) {
+    if (!e->opt_profile) return;
+    ProfEntry pe;
+    pe.name = name;
+    pe.flops = flops;
+    cudaEventCreate(&pe.a);
+    cudaEventCreate(&pe.b);
+    cudaEventRecord(pe.a, st);
+    e->prof.push_back(pe);
+    idx = (int)e->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(e->prof[idx].b, st);
+  }
+};
+
+int run_gemm(ssr_engine* e, const GemmOp& op, cudaStream_t st, const char* name = "gemm") {
   e->launches += e->opt_simt ? (op.epi.pool_part ? 2 : 1) : 1;
+  ProfScope ps(e, st, name, 2.0 * (double)op.M * (double)op.N * (double)op.K);
   return launch_gemm(op, st, e->opt_simt != 0, e->num_sms, e->err);
+}
+
+int run_ln(ssr_engine* e, const LayerNormArgs& a, cudaStream_t st) {
+  e->launches++;
+  ProfScope ps(e, st, a.gelu ? "layernorm_gelu" : "layernorm");
+  return launch_layernorm(a, st, e->err);
+}
+int run_attn(ssr_engine* e, const AttentionArgs& a, cudaStream_t st) {
+  e->launches++;
+  // QK^T and PV: 2 * 2 * T^2 * 64 per head (T = slot; masked keys are still multiplied)
+  ProfScope ps(e, st, "attention", 4.0 * (double)a.B * a.H * (double)a.slot * a.slot * 64.0);
+  return launch_attention(a, st, e->err);
 }
 
 GemmOp linear_op(const bf16* A, int M, int K, const bf16* W, int N, const EpiParams& ep) {
@@ -497,6 +539,7 @@ int wavlm_frames(int n) {
 int pool_into(ssr_engine* e, const float* x, int B, int slot, int D, float* pooled, int layer, int L1,
               cudaStream_t st) {
   e->launches += 1;
+  ProfScope ps(e, st, "pool_mean");
   return launch_pool_mean(x, B, slot, D, e->lens_dev.as<int>(), pooled + (long long)layer * D, (long long)L1 * D, st,
                           e->err);
 }
@@ -543,14 +586,13 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
         a.gate_const = W.gate_const;
         a.n_heads = H;
       }
-      e->launches++;
-      if (launch_layernorm(a, st, err)) return -1;
+      if (run_ln(e, a, st)) return -1;
     }
     // (post-LN: xn / gate for this layer were produced by the previous LayerNorm)
     if (snap && snapshot(e, 0, "L.attn_in", xn, 1, M, D, st)) return -1;
     if (snap && wavlm && snapshot(e, 1, "L.gate", gate, 0, M, H, st)) return -1;
     if (run_gemm(e, linear_op(xn, M, D, W.wqkv, 3 * D, epi_plain(W.bqkv, ACT_NONE, nullptr, 0, nullptr, 0, qkv, 3 * D)),
-                 st))
+                 st, "gemm_qkv"))
       return -1;
     if (snap && snapshot(e, 2, "L.qkv", qkv, 1, M, 3 * D, st)) return -1;
     {
@@ -569,12 +611,11 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
         a.rel_stride = 2 * e->rel_R - 1;
         a.rel_center = e->rel_R - 1;
       }
-      e->launches++;
-      if (launch_attention(a, st, err)) return -1;
+      if (run_attn(e, a, st)) return -1;
     }
     if (snap && snapshot(e, 3, "L.ctx", ctx, 1, M, D, st)) return -1;
     if (pre_ln) {
-      if (run_gemm(e, linear_op(ctx, M, D, W.wo, D, epi_plain(W.bo, ACT_NONE, h, D, h, D, nullptr, 0)), st)) return -1;
+      if (run_gemm(e, linear_op(ctx, M, D, W.wo, D, epi_plain(W.bo, ACT_NONE, h, D, h, D, nullptr, 0)), st, "gemm_out")) return -1;
       if (snap && snapshot(e, 4, "L.h_attn", h, 0, M, D, st)) return -1;
       LayerNormArgs a;
       memset(&a, 0, sizeof(a));
@@ -587,9 +628,8 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
       a.eps = 1e-5f;
       a.out_bf16 = xn;
       a.ld_out16 = D;
-      e->launches++;
-      if (launch_layernorm(a, st, err)) return -1;
-      if (run_gemm(e, linear_op(xn, M, D, W.w1, F, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, F)), st))
+      if (run_ln(e, a, st)) return -1;
+      if (run_gemm(e, linear_op(xn, M, D, W.w1, F, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, F)), st, "gemm_ffn1"))
         return -1;
       if (snap && snapshot(e, 5, "L.mid", mid, 1, M, F, st)) return -1;
       EpiParams ep = epi_plain(W.b2, ACT_NONE, h, D, h, D, nullptr, 0);
@@ -599,11 +639,12 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
         ep.pool_slot = slot;
         ep.lens = lens;
       }
-      if (run_gemm(e, linear_op(mid, M, F, W.w2, D, ep), st)) return -1;
+      if (run_gemm(e, linear_op(mid, M, F, W.w2, D, ep), st, "gemm_ffn2")) return -1;
       if (snap && snapshot(e, 6, "L.h_out", h, 0, M, D, st)) return -1;
       if (pool_here) {
         if (fused) {
           e->launches++;
+          ProfScope ps(e, st, "pool_finalize");
           if (launch_pool_finalize(part, B, slot, D, lens, pooled + (long long)(l + 1) * D, (long long)L1 * D, st, err))
             return -1;
         } else if (pool_into(e, h, B, slot, D, pooled, l + 1, L1, st)) {
@@ -612,7 +653,7 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
       }
     } else {
       // post-LN (WavLM Base+)
-      if (run_gemm(e, linear_op(ctx, M, D, W.wo, D, epi_plain(W.bo, ACT_NONE, h, D, tmp, D, nullptr, 0)), st))
+      if (run_gemm(e, linear_op(ctx, M, D, W.wo, D, epi_plain(W.bo, ACT_NONE, h, D, tmp, D, nullptr, 0)), st, "gemm_out"))
         return -1;
       LayerNormArgs a;
       memset(&a, 0, sizeof(a));
@@ -627,13 +668,12 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
       a.ld_out32 = D;
       a.out_bf16 = xn;
       a.ld_out16 = D;
-      e->launches++;
-      if (launch_layernorm(a, st, err)) return -1;
+      if (run_ln(e, a, st)) return -1;
       if (snap && snapshot(e, 4, "L.h_attn", h, 0, M, D, st)) return -1;
-      if (run_gemm(e, linear_op(xn, M, D, W.w1, F, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, F)), st))
+      if (run_gemm(e, linear_op(xn, M, D, W.w1, F, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, F)), st, "gemm_ffn1"))
         return -1;
       if (snap && snapshot(e, 5, "L.mid", mid, 1, M, F, st)) return -1;
-      if (run_gemm(e, linear_op(mid, M, F, W.w2, D, epi_plain(W.b2, ACT_NONE, h, D, tmp, D, nullptr, 0)), st))
+      if (run_gemm(e, linear_op(mid, M, F, W.w2, D, epi_plain(W.b2, ACT_NONE, h, D, tmp, D, nullptr, 0)), st, "gemm_ffn2"))
         return -1;
       memset(&a, 0, sizeof(a));
       a.in_f32 = tmp;
@@ -657,8 +697,7 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
         a.gate_const = Wn.gate_const;
         a.n_heads = H;
       }
-      e->launches++;
-      if (launch_layernorm(a, st, err)) return -1;
+      if (run_ln(e, a, st)) return -1;
       if (snap && snapshot(e, 6, "L.h_out", h, 0, M, D, st)) return -1;
       if (pool_into(e, h, B, slot, D, pooled, l + 1, L1, st)) return -1;
     }
@@ -676,8 +715,7 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
     a.eps = 1e-5f;
     a.out_f32 = tmp;
     a.ld_out32 = D;
-    e->launches++;
-    if (launch_layernorm(a, st, err)) return -1;
+    if (run_ln(e, a, st)) return -1;
     if (pool_into(e, tmp, B, slot, D, pooled, L, L1, st)) return -1;
     reg_dbg(e, "last_hidden", tmp, 0, M, D);
   } else {
@@ -775,7 +813,10 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     a.out = e->conv[0].as<bf16>();
     a.slot0 = slots[0];
     e->launches += a.mode == 0 ? 2 : 4;
-    if (launch_wavlm_conv0(a, st, err)) return -1;
+    {
+      ProfScope ps(e, st, "wavlm_conv0", 2.0 * 10 * 512 * (double)B * slots[0]);
+      if (launch_wavlm_conv0(a, st, err)) return -1;
+    }
     reg_dbg(e, "conv0", e->conv[0].p, 1, B, slots[0], 512);
   }
   // 2. conv layers 1..6 as implicit GEMMs over the channels-last signal
@@ -793,7 +834,7 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     op.a_cols = 0;
     const bool ln = d.feat_norm == SSR_FEAT_NORM_LAYER;
     op.epi = epi_plain(nullptr, ln ? ACT_NONE : ACT_GELU, nullptr, 0, nullptr, 0, e->conv[i].as<bf16>(), 512);
-    if (run_gemm(e, op, st)) return -1;
+    if (run_gemm(e, op, st, "gemm_conv")) return -1;
     if (ln) {
       LayerNormArgs a;
       memset(&a, 0, sizeof(a));
@@ -807,8 +848,7 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
       a.gelu = 1;
       a.out_bf16 = e->conv[i].as<bf16>();
       a.ld_out16 = 512;
-      e->launches++;
-      if (launch_layernorm(a, st, err)) return -1;
+      if (run_ln(e, a, st)) return -1;
     }
     char nm[16];
     snprintf(nm, sizeof nm, "conv%d", i);
@@ -827,20 +867,23 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     a.eps = 1e-5f;
     a.out_bf16 = e->feat_ln.as<bf16>();
     a.ld_out16 = 512;
-    e->launches++;
-    if (launch_layernorm(a, st, err)) return -1;
+    if (run_ln(e, a, st)) return -1;
     if (run_gemm(e,
                  linear_op(e->feat_ln.as<bf16>(), M, 512, e->fp_w, D,
                            epi_plain(e->fp_b, ACT_NONE, nullptr, 0, e->feat.as<float>(), D, nullptr, 0)),
-                 st))
+                 st, "gemm_proj"))
       return -1;
     reg_dbg(e, "feat", e->feat.p, 0, B, slot, D);
   }
   // 4. positional conv embedding (grouped conv k=128 as 16 block-diagonal GEMMs with K = 128 taps x 64 channels)
   {
     e->launches++;
-    if (launch_posconv_pack(e->feat.as<float>(), B, slot, D, e->lens_dev.as<int>(), e->xp.as<bf16>(), pslot, st, err))
-      return -1;
+    {
+      ProfScope ps(e, st, "posconv_pack");
+      if (launch_posconv_pack(e->feat.as<float>(), B, slot, D, e->lens_dev.as<int>(), e->xp.as<bf16>(), pslot, st,
+                              err))
+        return -1;
+    }
     GemmOp op;
     op.A = e->xp.as<bf16>();
     op.lda = 1024;
@@ -852,13 +895,16 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     op.a_mode = 1;
     op.a_cols = 1024;
     op.epi = epi_plain(nullptr, ACT_NONE, nullptr, 0, e->posconv.as<float>(), 1024, nullptr, 0);
-    if (run_gemm(e, op, st)) return -1;
+    if (run_gemm(e, op, st, "gemm_posconv")) return -1;
     const bool stable = d.stable_ln != 0;
     float* dst = stable ? e->h.as<float>() : e->tmp.as<float>();
     e->launches++;
-    if (launch_posconv_finish(e->posconv.as<float>(), pslot, e->pos_b, e->feat.as<float>(), B, slot, D,
-                              e->lens_dev.as<int>(), dst, st, err))
-      return -1;
+    {
+      ProfScope ps(e, st, "posconv_finish");
+      if (launch_posconv_finish(e->posconv.as<float>(), pslot, e->pos_b, e->feat.as<float>(), B, slot, D,
+                                e->lens_dev.as<int>(), dst, st, err))
+        return -1;
+    }
     if (!stable) {
       // Base+: encoder.layer_norm right after the positional add; its output is hidden_states[0]
       LayerNormArgs a;
@@ -882,8 +928,7 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
       a.gate_bb = W0.gate_bb;
       a.gate_const = W0.gate_const;
       a.n_heads = H;
-      e->launches++;
-      if (launch_layernorm(a, st, err)) return -1;
+      if (run_ln(e, a, st)) return -1;
     }
     if (pool_into(e, e->h.as<float>(), B, slot, D, pooled, 0, L1, st)) return -1;
     if (e->opt_snapshot_layer >= 0 && snapshot(e, 7, "hs0", e->h.p, 0, M, D, st)) return -1;
@@ -925,6 +970,7 @@ int whisper_logmel(ssr_engine* e, const float* audio, int64_t audio_ld, const in
   a.mel_out = mel_out;
   a.conv_in = want_conv_in ? e->conv_in.as<bf16>() : nullptr;
   e->launches += 3;
+  ProfScope ps(e, st, "logmel");
   return launch_logmel(a, st, err);
 }
 
@@ -966,7 +1012,7 @@ int whisper_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const i
     op.epi.out_slot = 3002;
     op.epi.valid = 3000;
     op.epi.out_off = 1;
-    if (run_gemm(e, op, st)) return -1;
+    if (run_gemm(e, op, st, "gemm_conv1")) return -1;
     reg_dbg(e, "c1", e->c1.p, 1, B, 3002, D);
   }
   // conv2: k=3, stride 2, pad=1; GELU; + embed_positions; this is hidden_states[0]
@@ -989,9 +1035,10 @@ int whisper_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const i
     op.epi.resid_by_t = 1;
     const bool fused = e->opt_fused_pool != 0;
     if (fused) op.epi.pool_part = e->pool_part.as<float>();
-    if (run_gemm(e, op, st)) return -1;
+    if (run_gemm(e, op, st, "gemm_conv2")) return -1;
     if (fused) {
       e->launches++;
+      ProfScope ps(e, st, "pool_finalize");
       if (launch_pool_finalize(e->pool_part.as<float>(), B, 1501, D, e->lens_dev.as<int>(), pooled,
                                (long long)L1 * D, st, err))
         return -1;
@@ -1087,6 +1134,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_fused_pool = value;
   else if (k == "snapshot_layer")
     e->opt_snapshot_layer = value;
+  else if (k == "profile")
+    e->opt_profile = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;
@@ -1294,6 +1343,41 @@ int ssr_pool_mean(const float* x, int32_t B, int32_t slot, int32_t D, const int3
   int rc = launch_pool_mean(x, B, slot, D, lens_dev, pooled, pooled_ld, as_stream(cuda_stream), err);
   if (rc) copy_err(err, errbuf, err_len);
   return rc;
+}
+
+const char* ssr_profile_fetch(ssr_engine* e) {
+  if (!e) return nullptr;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  struct Agg {
+    double ms = 0, flops = 0;
+    long n = 0;
+  };
+  std::map<std::string, Agg> agg;
+  for (ProfEntry& pe : e->prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+      Agg& g = agg[pe.name];
+      g.ms += ms;
+      g.flops += pe.flops;
+      g.n += 1;
+    }
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  e->prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %ld, \"ms\": %.6f, \"flops\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  e->prof_json = js;
+  return e->prof_json.c_str();
 }
 
 int64_t ssr_debug_fetch(ssr_engine* e, const char* name, void* dst_host, int64_t dst_bytes, int64_t* dims,

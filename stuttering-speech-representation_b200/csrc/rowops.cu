@@ -130,12 +130,14 @@ int launch_layernorm(const LayerNormArgs& a, cudaStream_t st, std::string& err) 
       layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(a);               \
     break;
   switch (a.D) {
+    SSR_LN_CASE(2)
+    SSR_LN_CASE(3)
     SSR_LN_CASE(4)
     SSR_LN_CASE(6)
     SSR_LN_CASE(8)
     SSR_LN_CASE(10)
     default:
-      err = "layernorm: unsupported width " + std::to_string(a.D) + " (supported: 512, 768, 1024, 1280)";
+      err = "layernorm: unsupported width " + std::to_string(a.D) + " (supported: 256, 384, 512, 768, 1024, 1280)";
       return -1;
   }
 #undef SSR_LN_CASE

@@ -83,6 +83,13 @@ class _EngineBase:
     def launch_count(self) -> int:
         return int(self._lib.ssr_launch_count(self._h))
 
+    def profile_fetch(self) -> dict:
+        """Per-kernel-group device-event times since the last fetch (needs set_option('profile', 1))."""
+        import json
+
+        s = self._lib.ssr_profile_fetch(self._h)
+        return json.loads(s.decode()) if s else {}
+
     def debug_fetch(self, name: str) -> np.ndarray:
         """Copy a named internal buffer of the last run (bf16 buffers are returned as float32)."""
         dims = (C.c_int64 * 4)()
@@ -135,6 +142,18 @@ class _EngineBase:
             out = torch.empty((B, self.layers + 1, self.hidden), dtype=torch.float32, device=audio.device)
         self._call_dev(self._pooled_fn, audio, np.asarray(n_samples, dtype=np.int32), out, stream)
         return out
+
+    def pooled_pinned(self, audio_host: torch.Tensor, n_samples, out_host: torch.Tensor) -> torch.Tensor:
+        """Host buffers in and out through the C ABI's *_host entry point (H2D, run, D2H, stream sync inside).
+        Pass pinned tensors for full PCIe speed: audio_host float32 [B, ld], out_host float32 [B, L+1, D]."""
+        assert not audio_host.is_cuda and audio_host.dtype == torch.float32 and audio_host.stride(1) == 1
+        assert not out_host.is_cuda and out_host.dtype == torch.float32 and out_host.is_contiguous()
+        n = np.ascontiguousarray(n_samples, dtype=np.int32)
+        rc = self._pooled_host_fn(self._h, audio_host.data_ptr(), audio_host.stride(0), n.ctypes.data_as(_lib.c_i32p),
+                                  audio_host.shape[0], out_host.data_ptr())
+        if rc != 0:
+            raise SsrError(self._err())
+        return out_host
 
     def pooled(self, clips: Sequence) -> np.ndarray:
         """Host in, host out (the call the drop-in shim makes): list of 1-D float clips -> float32 [B, L+1, D]."""

@@ -54,9 +54,10 @@ def get_engine(model, feature_extractor=None, device=0):
 def _device_index(device) -> int:
     if isinstance(device, int):
         return device
-    idx = getattr(device, "index", None)
-    if idx is not None:
-        return int(idx)
+    if not isinstance(device, str):
+        idx = getattr(device, "index", None)  # torch.device
+        if isinstance(idx, int):
+            return idx
     s = str(device)
     return int(s.split(":")[1]) if ":" in s else 0
 

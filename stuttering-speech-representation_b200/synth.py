@@ -1,0 +1,102 @@
+"""Synthetic workloads shared by tests, bench.py and tools/make_golden.py: model configs (checkpoints are
+unavailable offline, so weights are seeded random-init of the published architectures) and
+seeded synthetic audio. `transformers` is imported lazily and only to *instantiate the reference-side model
+objects* that the engine is built from — exactly what a user of the reference scripts already holds.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SR = 16000
+
+
+def noise_clips(n_clips: int, n_samples: int = 48000, seed: int = 1234, sigma: float = 0.1) -> list[np.ndarray]:
+    """np.random.default_rng(seed).standard_normal(n) * 0.1, one draw per clip."""
+    rng = np.random.default_rng(seed)
+    return [(rng.standard_normal(n_samples).astype(np.float32) * np.float32(sigma)) for _ in range(n_clips)]
+
+
+def tonal_clip(n_samples: int = 48000, f0: float = 440.0) -> np.ndarray:
+    """440 Hz tone with harmonics, a silence gap and a quiet tail — exercises the Whisper (max - 8) clamp."""
+    t = np.arange(n_samples, dtype=np.float64) / SR
+    x = 0.3 * np.sin(2 * np.pi * f0 * t) + 0.05 * np.sin(2 * np.pi * 3 * f0 * t + 0.3)
+    x[n_samples // 3: n_samples // 2] = 0.0
+    x[-n_samples // 8:] *= 1e-3
+    return x.astype(np.float32)
+
+
+def clip_by_index(index: int, n_samples: int = 48000, seed: int = 1234) -> np.ndarray:
+    """Counter-keyed clip: any sharding reproduces the same clip for a global index."""
+    rng = np.random.default_rng([seed, int(index)])
+    return rng.standard_normal(n_samples).astype(np.float32) * np.float32(0.1)
+
+
+def mixed_clips() -> list[np.ndarray]:
+    """Ragged, tonal and silent clips for edge-case parity."""
+    a = noise_clips(3, 48000, seed=7)
+    return [a[0], a[1][:40000], tonal_clip(48000), a[2][:16000], np.zeros(32000, np.float32)]
+
+
+# ------------------------------------------------------------------------------------------------ model configs
+def wavlm_config(name: str):
+    from transformers import WavLMConfig
+
+    if name == "base_plus":  # == WavLMConfig() defaults (HF configuration_wavlm.py:159-183)
+        return WavLMConfig()
+    if name == "large":
+        return WavLMConfig(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                           feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
+    if name == "tiny_stable":  # small pre-LN variant for fast tests
+        return WavLMConfig(hidden_size=512, num_hidden_layers=3, num_attention_heads=8, intermediate_size=1024,
+                           feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
+    if name == "tiny_post":  # small post-LN / GroupNorm variant
+        return WavLMConfig(hidden_size=768, num_hidden_layers=2, num_attention_heads=12, intermediate_size=1024)
+    raise KeyError(name)
+
+
+def wavlm_do_normalize(name: str) -> bool:
+    return name in ("large", "tiny_stable")
+
+
+def whisper_config(name: str):
+    from transformers import WhisperConfig
+
+    if name == "large":
+        return WhisperConfig(d_model=1280, encoder_layers=32, encoder_attention_heads=20, encoder_ffn_dim=5120,
+                             decoder_layers=32, decoder_attention_heads=20, decoder_ffn_dim=5120, num_mel_bins=80,
+                             vocab_size=51865)
+    if name == "tiny":  # small config for fast tests (d_model must be a multiple of 256, head_dim 64)
+        return WhisperConfig(d_model=256, encoder_layers=2, encoder_attention_heads=4, encoder_ffn_dim=1024,
+                             decoder_layers=1, decoder_attention_heads=4, decoder_ffn_dim=256, num_mel_bins=80,
+                             vocab_size=1000)
+    raise KeyError(name)
+
+
+def build_wavlm(name: str, seed: int = 0):
+    """(model, feature_extractor) as the reference holds them (REF/WavLM_embeddings.py:482-483), random init."""
+    import torch
+    from transformers import Wav2Vec2FeatureExtractor, WavLMModel
+
+    torch.manual_seed(seed)
+    model = WavLMModel(wavlm_config(name)).eval()
+    fe = Wav2Vec2FeatureExtractor(do_normalize=wavlm_do_normalize(name))
+    return model, fe
+
+
+def build_whisper_encoder(name: str, seed: int = 0):
+    """(encoder, feature_extractor): encoder-only instantiation of the Whisper architecture, random init."""
+    import torch
+    from transformers import WhisperFeatureExtractor
+    from transformers.models.whisper.modeling_whisper import WhisperEncoder
+
+    torch.manual_seed(seed)
+    enc = WhisperEncoder(whisper_config(name)).eval()
+    return enc, WhisperFeatureExtractor()
+
+
+def state_checksum(model) -> float:
+    """Cheap fingerprint of seeded weights (guards golden fixtures against RNG drift)."""
+    import torch
+
+    with torch.no_grad():
+        return float(sum(p.double().abs().sum() for p in model.state_dict().values() if p.dtype.is_floating_point))
