@@ -64,6 +64,7 @@ void ssr_destroy(ssr_engine* e);
 const char* ssr_last_error(const ssr_engine* e);
 
 /* Options: "simt_gemm" (bring-up cross-check GEMM), "fused_pool" (default 1), "snapshot_layer" (-1 = off),
+ * "attn_simt" (1 = mma.sync attention cross-check kernel),
  * "profile" (1 = bracket every kernel launch with CUDA events on the launching stream; read with ssr_profile_fetch).
  * Returns 0, or -1 for an unknown key. */
 int ssr_set_option(ssr_engine* e, const char* key, int32_t value);
@@ -113,10 +114,12 @@ int ssr_gemm_bf16_pool(int32_t cuda_device, const void* A, int64_t lda, const vo
 int ssr_layernorm(const float* in_f32, const void* in_bf16, int64_t rows, int32_t D, const float* gamma,
                   const float* beta, int32_t gelu, float* out_f32, void* out_bf16, void* cuda_stream, char* err,
                   int32_t err_len);
-/* Self-attention over fused qkv [B*slot, 3*D] bf16 (q pre-scaled), optional WavLM gated relative bias. */
+/* Self-attention over fused qkv [B*slot, 3*D] bf16 (q pre-scaled), optional WavLM gated relative bias
+ * (relbias [H, rel_stride] must cover relative positions +-roundup(slot, 128) around rel_center).
+ * impl: 0 = tcgen05/TMEM kernel (the product path), 1 = mma.sync cross-check kernel. */
 int ssr_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t slot, int32_t H, const int32_t* lens_dev,
-                  const float* gate, const float* relbias, int32_t rel_stride, int32_t rel_center, void* cuda_stream,
-                  char* err, int32_t err_len);
+                  const float* gate, const float* relbias, int32_t rel_stride, int32_t rel_center, int32_t impl,
+                  void* cuda_stream, char* err, int32_t err_len);
 /* pooled[b, :] = mean over t < lens[b] of x[b*slot + t, :]. */
 int ssr_pool_mean(const float* x, int32_t B, int32_t slot, int32_t D, const int32_t* lens_dev, float* pooled,
                   int64_t pooled_ld, void* cuda_stream, char* err, int32_t err_len);

@@ -48,7 +48,8 @@ SIGNATURES = {
     "ssr_gemm_bf16_pool": (c_i32, [c_i32, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_i32,
                                    c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_cp, c_i32]),
     "ssr_layernorm": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_cp, c_i32]),
-    "ssr_attention": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_cp, c_i32]),
+    "ssr_attention": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_cp,
+                              c_i32]),
     "ssr_pool_mean": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_cp, c_i32]),
     "ssr_debug_fetch": (c_i64, [c_vp, c_cp, c_vp, c_i64, c_i64p, c_i32p]),
 }

@@ -55,6 +55,10 @@ struct GemmOp {
 // ---- launchers (each returns cudaError_t / sets message in err) ----
 int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err);
 
+// 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows of pitch `pitch_elems`; box = 64 x box_rows; 128-byte swizzle.
+int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsigned long long dim1,
+                 unsigned long long pitch_elems, unsigned box_rows, std::string& err);
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace ssr

@@ -99,7 +99,7 @@ struct ssr_engine {
   std::string err;
   int64_t launches = 0;
   // options
-  int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1, opt_profile = 0;
+  int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1, opt_profile = 0, opt_attn_simt = 0;
   std::vector<ProfEntry> prof;
   std::string prof_json;
 
@@ -485,7 +485,7 @@ int run_attn(ssr_engine* e, const AttentionArgs& a, cudaStream_t st) {
   e->launches++;
   // QK^T and PV: 2 * 2 * T^2 * 64 per head (T = slot; masked keys are still multiplied)
   ProfScope ps(e, st, "attention", 4.0 * (double)a.B * a.H * (double)a.slot * a.slot * 64.0);
-  return launch_attention(a, st, e->err);
+  return e->opt_attn_simt ? launch_attention(a, st, e->err) : launch_attention_tc(a, st, e->err);
 }
 
 GemmOp linear_op(const bf16* A, int M, int K, const bf16* W, int N, const EpiParams& ep) {
@@ -1136,6 +1136,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_snapshot_layer = value;
   else if (k == "profile")
     e->opt_profile = value;
+  else if (k == "attn_simt")
+    e->opt_attn_simt = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;
@@ -1316,8 +1318,8 @@ int ssr_layernorm(const float* in_f32, const void* in_bf16, int64_t rows, int32_
 }
 
 int ssr_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t slot, int32_t H, const int32_t* lens_dev,
-                  const float* gate, const float* relbias, int32_t rel_stride, int32_t rel_center, void* cuda_stream,
-                  char* errbuf, int32_t err_len) {
+                  const float* gate, const float* relbias, int32_t rel_stride, int32_t rel_center, int32_t impl,
+                  void* cuda_stream, char* errbuf, int32_t err_len) {
   std::string err;
   AttentionArgs a;
   memset(&a, 0, sizeof(a));
@@ -1332,7 +1334,7 @@ int ssr_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t slot,
   a.relbias = relbias;
   a.rel_stride = rel_stride;
   a.rel_center = rel_center;
-  int rc = launch_attention(a, as_stream(cuda_stream), err);
+  int rc = impl == 0 ? launch_attention_tc(a, as_stream(cuda_stream), err) : launch_attention(a, as_stream(cuda_stream), err);
   if (rc) copy_err(err, errbuf, err_len);
   return rc;
 }

@@ -399,7 +399,7 @@ static PFN_encodeTiled get_encode_fn(std::string& err) {
 }
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1 with row pitch `pitch_elems`; box = 64 x box_rows; 128B swizzle.
-static int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsigned long long dim1,
+int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsigned long long dim1,
                         unsigned long long pitch_elems, unsigned box_rows, std::string& err) {
   PFN_encodeTiled enc = get_encode_fn(err);
   if (!enc) return -1;

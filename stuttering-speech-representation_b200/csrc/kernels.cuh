@@ -49,7 +49,8 @@ struct AttentionArgs {
   const float* relbias;
   int rel_stride, rel_center;
 };
-int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);
+int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);      // mma.sync (debug / tiny T)
+int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
 
 // WavLM waveform statistics + first conv layer (C_in = 1, k = 10, stride 5) fused with its normalisation + GELU.
 struct Conv0Args {

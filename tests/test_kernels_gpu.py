@@ -165,11 +165,13 @@ def _attn_ref(qkv, B, slot, H, lens, gate, relbias, rel_center):
     return o.transpose(1, 2).reshape(B * slot, D)
 
 
+@pytest.mark.parametrize("impl", [0, 1], ids=["tc", "mma"])
 @pytest.mark.parametrize("slot,H,lens,bias", [
     (149, 16, None, True), (150, 12, [149, 77, 150], True), (200, 4, [200, 64, 65], False), (1500, 2, None, False),
-    (31, 3, [31, 5, 1], True),
+    (31, 3, [31, 5, 1], True), (128, 2, [128, 127, 1], True), (257, 2, [257, 256, 129], True),
+    (1500, 2, [1500, 1400, 300], True),
 ])
-def test_attention(slot, H, lens, bias):
+def test_attention(slot, H, lens, bias, impl):
     lib = _lib()
     B = 3
     D = H * 64
@@ -186,7 +188,7 @@ def test_attention(slot, H, lens, bias):
     out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
     e = _err()
     rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), _ptr(gate), _ptr(relb),
-                           2 * R - 1, R - 1, None, e, 512)
+                           2 * R - 1, R - 1, impl, None, e, 512)
     torch.cuda.synchronize()
     assert rc == 0, e.value.decode()
     ref = _attn_ref(qkv, B, slot, H, lens_t, gate, relb, R - 1).view(B, slot, D)
