@@ -1,9 +1,10 @@
 // Flash-style multi-head self-attention on the 5th-gen tensor cores (sm_100a), head_dim 64.
 //
 //   per CTA: one (clip, head, 128-query tile); loop over 128-key blocks
-//     warp 0      TMA producer: Q once, then K_j / V_j tiles (double buffered) straight out of the fused qkv matrix
-//     warp 1      single-thread tcgen05.mma issuer:  S = Q K_j^T  -> TMEM[0,128) ;  PV_j = P_j V_j -> TMEM[128,192)
-//     warps 2-5   softmax: thread = query row (TMEM lane). tcgen05.ld S, + gated relative-position bias, key mask,
+//     warp 4      TMA producer: Q once, then K_j / V_j tiles (double buffered) straight out of the fused qkv matrix
+//     warp 5      single-thread tcgen05.mma issuer:  S = Q K_j^T  -> TMEM[0,128) ;  PV_j = P_j V_j -> TMEM[128,192)
+//                 (driver warps carry the highest warp ids: the sub-partition arbiter favours them over softmax warps)
+//     warps 0-3   softmax: thread = query row (TMEM lane). tcgen05.ld S, + gated relative-position bias, key mask,
 //                 online max / sum in fp32, P (bf16) written to shared memory in the UMMA 128B-swizzled K-major
 //                 layout; after PV_j completes the partial product is folded into the fp32 O accumulator kept in
 //                 registers (so no TMEM read-modify-write is needed for the online-softmax rescale).
@@ -85,7 +86,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 5) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -94,7 +95,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 128) {
     // ============================ TMA producer ============================
     mbar_arrive_expect_tx(bar_q, TILE_BYTES);
     tma_load_2d(smem + SM_Q, &tm, bar_q, h * HD, row0 + q0);
@@ -106,7 +107,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
       tma_load_2d(smem + SM_KV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * a.D + h * HD,
                   row0 + j * KBLK);
     }
-  } else if (threadIdx.x == 32) {
+  } else if (threadIdx.x == 160) {
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
@@ -134,9 +135,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
       umma_commit(&kv_empty[s]);
       umma_commit(bar_o);
     }
-  } else if (warp >= 2) {
+  } else if (warp < 4) {
     // ============================ softmax / output warps ============================
-    const uint32_t quad = warp & 3;               // TMEM lane quadrant accessible to this warp
+    const uint32_t quad = warp;                   // TMEM lane quadrant accessible to this warp
     const int il = quad * 32 + lane;              // query row inside the tile
     const int i = q0 + il;                        // query index inside the clip
     const uint32_t lane_addr = (quad * 32u) << 16;
@@ -253,7 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }

@@ -59,6 +59,26 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, s
 int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsigned long long dim1,
                  unsigned long long pitch_elems, unsigned box_rows, std::string& err);
 
+#ifdef __CUDACC__
+// erf-GELU with erfc(|z|) from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 / fp32-residual
+// noise floor of the consumers) : 2 MUFU ops + ~10 FMA instead of libdevice erff's two-branch polynomial.
+//   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt(2))
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  float ex;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));
+  const float q = pl * t * ex;  // erfc(z)
+  return fmaxf(x, 0.0f) - 0.5f * ax * q;
+}
+
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace ssr

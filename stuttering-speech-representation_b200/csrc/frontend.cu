@@ -182,7 +182,7 @@ wavlm_conv0_kernel(const Conv0Args a) {
           y0 = (acc[i][0][j] - (float)m0) * r0 * g.x + be.x;
           y1 = (acc[i][1][j] - (float)m1) * r1 * g.y + be.y;
         }
-        __nv_bfloat162 p = __floats2bfloat162_rn(gelu_f(y0), gelu_f(y1));
+        __nv_bfloat162 p = __floats2bfloat162_rn(gelu_fast(y0), gelu_fast(y1));
         *reinterpret_cast<__nv_bfloat162*>(dst + c) = p;
       }
     }

@@ -1,15 +1,20 @@
 // bf16 GEMM for sm_100a:  C[M,N] = A[M,K] · W[N,K]^T  with a fused epilogue (bias, erf-GELU, fp32 residual,
 // slot-remapped stores, fused per-clip time pooling partial sums).
 //
-// Main path: persistent warp-specialised kernel — TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring ->
+// Main path: persistent warp-specialised kernels — TMA (cp.async.bulk.tensor, 128B swizzle) -> smem ring ->
 // tcgen05.mma (one issuing thread, fp32 accumulators in TMEM, double buffered) -> tcgen05.ld epilogue warps.
+//   * gemm_tc2_kernel : CTA pair (cta_group::2), 256 x 256 output tile per SM pair — every large GEMM (N % 256 == 0)
+//   * gemm_tc_kernel  : single CTA, 128 x {64,128,256} tile — the positional conv (block-diagonal, N tile 64) and
+//                       odd shapes
 // Every Linear layer of the WavLM / Whisper encoders and every Conv1d (as an implicit GEMM: the im2col matrix of a
 // channels-last signal is a 2-D view with row stride = conv_stride * C, which a TMA tensor map expresses directly)
-// runs through this kernel.  Reference arithmetic being replaced: torch F.linear / F.conv1d calls inside
+// runs through these kernels.  Reference arithmetic being replaced: torch F.linear / F.conv1d calls inside
 // HF/models/wavlm/modeling_wavlm.py:93-105,188-241,288-295,682-789 and HF/models/whisper/modeling_whisper.py:284-414,619-625.
 //
-// A second, deliberately naive SIMT kernel with an independent scalar epilogue exists only for bring-up
-// cross-checks (SSR_DEBUG_SIMT_GEMM=1); it is never selected otherwise.
+// A deliberately naive SIMT kernel with an independent scalar epilogue exists only for bring-up cross-checks
+// (engine option "simt_gemm"); it is never selected otherwise.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -64,18 +69,44 @@ __device__ __forceinline__ void warp_colsum32(float (&v)[32], uint32_t lane) {
   }
 }
 
-// One 32-column chunk of one output row, values in registers.
-__device__ __forceinline__ void epi_chunk(const EpiParams& e, int N, const RowInfo& ri, int group, int col0,
-                                          uint32_t (&raw)[32], uint32_t lane) {
+// ------------------------------------------------------------------------------------------------ epilogue
+// Per-warp staging area. The accumulator arrives thread-per-row (TMEM lane = output row); global memory wants
+// row-contiguous accesses. A 32 x 32 fp32 chunk is transposed through `tile` (pitch 36 floats: 16-byte aligned,
+// bank-spread) so that every global load / store instruction touches whole 128-byte (fp32) or 64-byte (bf16) row
+// segments. `orow` / `rrow` hold the routed output / residual row of the warp's 32 rows (-1 = dead row) and `bias`
+// the tile's bias slice, fetched once per tile BEFORE the accumulator is waited for (no load latency per chunk).
+constexpr int STG_LD = 36;
+struct __align__(16) EpiStage {
+  float tile[32 * STG_LD];
+  float bias[256];
+  int orow[32];
+  int rrow[32];
+};
+
+// Coalesced residual fetch for one 32-column chunk (4 rows x 128 contiguous bytes per instruction), issued one chunk
+// ahead of its use so that the HBM latency overlaps the previous chunk's work.
+__device__ __forceinline__ void load_resid(const EpiParams& e, const EpiStage& st, int col0, uint32_t lane,
+                                           float4 (&x)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = st.rrow[it * 4 + (lane >> 3)];
+    x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rr >= 0) x[it] = *reinterpret_cast<const float4*>(e.resid + (long long)rr * e.ldr + col0 + (lane & 7) * 4);
+  }
+}
+
+// One 32-column chunk of the warp's 32 output rows. `raw`: this thread's row of the accumulator; `x`: pre-fetched
+// residual chunk (coalesced layout); `bcol`: offset of the chunk inside the staged bias slice.
+__device__ __forceinline__ void epi_chunk(const EpiParams& e, int N, const RowInfo& ri, int group, int col0, int bcol,
+                                          uint32_t (&raw)[32], uint32_t lane, EpiStage& st, const float4 (&x)[8]) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
 
   if (e.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
+      const float4 b = *reinterpret_cast<const float4*>(&st.bias[bcol + i * 4]);  // warp-wide broadcast
       v[4 * i + 0] += b.x;
       v[4 * i + 1] += b.y;
       v[4 * i + 2] += b.z;
@@ -84,42 +115,64 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, int N, const RowIn
   }
   if (e.act == ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
-  if (e.resid != nullptr && ri.live) {
-    const long long rr = e.resid_by_t ? (long long)ri.t : ri.orow;
-    const float4* r4 = reinterpret_cast<const float4*>(e.resid + rr * e.ldr + col0);
+  if (e.resid != nullptr) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      *reinterpret_cast<float4*>(&st.tile[(it * 4 + (lane >> 3)) * STG_LD + (lane & 7) * 4]) = x[it];
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 b = r4[i];
+      const float4 b = *reinterpret_cast<const float4*>(&st.tile[lane * STG_LD + i * 4]);
       v[4 * i + 0] += b.x;
       v[4 * i + 1] += b.y;
       v[4 * i + 2] += b.z;
       v[4 * i + 3] += b.w;
     }
+    __syncwarp();
   }
-  if (ri.live) {
-    if (e.out_f32 != nullptr) {
-      float4* o4 = reinterpret_cast<float4*>(e.out_f32 + ri.orow * e.ldo32 + col0);
+  if (e.out_f32 != nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
-    if (e.out_bf16 != nullptr) {
-      uint4* o4 = reinterpret_cast<uint4*>(e.out_bf16 + ri.orow * e.ldo16 + col0);
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(&st.tile[lane * STG_LD + i * 4]) =
+          make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
-        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&p0);
-        u.y = *reinterpret_cast<uint32_t*>(&p1);
-        u.z = *reinterpret_cast<uint32_t*>(&p2);
-        u.w = *reinterpret_cast<uint32_t*>(&p3);
-        o4[i] = u;
-      }
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3);
+      const int orow = st.orow[row];
+      if (orow >= 0)
+        *reinterpret_cast<float4*>(e.out_f32 + (long long)orow * e.ldo32 + col0 + (lane & 7) * 4) =
+            *reinterpret_cast<const float4*>(&st.tile[row * STG_LD + (lane & 7) * 4]);
     }
+    __syncwarp();
+  }
+  if (e.out_bf16 != nullptr) {
+    // bf16 rows are 64 bytes; staged with an 80-byte pitch (20 floats)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i + 0], v[8 * i + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2);
+      u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(&st.tile[lane * 20 + i * 4]) = u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = it * 8 + (lane >> 2);
+      const int orow = st.orow[row];
+      if (orow >= 0)
+        *reinterpret_cast<uint4*>(e.out_bf16 + (long long)orow * e.ldo16 + col0 + (lane & 3) * 8) =
+            *reinterpret_cast<const uint4*>(&st.tile[row * 20 + (lane & 3) * 4]);
+    }
+    __syncwarp();
   }
   if (e.pool_part != nullptr) {
     // segment 0: rows of the clip that owns the group's first row; segment 1: rows of the following clip.
@@ -145,10 +198,48 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, int N, const RowIn
   }
 }
 
-// ------------------------------------------------------------------------------------------------ tcgen05 kernel
+// Epilogue of one output tile for one warp: 32 rows (TMEM lane quadrant `quad`, first row r0) x the 32-column chunks
+// c = split, split + NSPLIT, ... of the tile's BN columns (NSPLIT warps share a quadrant).
+template <int BN, int NSPLIT>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, EpiStage& stg, uint32_t tmem_acc, uint32_t quad,
+                                              int r0, int col_base, uint32_t lane, int split, uint64_t* tfull,
+                                              uint32_t parity) {
+  const RowInfo ri = route_row(p.epi, p.M, r0 + (int)lane);
+  const int group = r0 >> 5;
+  stg.orow[lane] = ri.live ? (int)ri.orow : -1;
+  stg.rrow[lane] = ri.live ? (p.epi.resid_by_t ? ri.t : (int)ri.orow) : -1;
+  if (p.epi.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) stg.bias[i * 32 + lane] = __ldg(p.epi.bias + col_base + i * 32 + lane);
+  }
+  __syncwarp();
+  const bool has_resid = p.epi.resid != nullptr;
+  float4 x[8], xn[8];
+  if (has_resid) load_resid(p.epi, stg, col_base + split * 32, lane, x);  // in flight while the MMAs finish
+  mbar_wait(tfull, parity);
+  __syncwarp();
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = split; c < BN / 32; c += NSPLIT) {
+    if (has_resid && c + NSPLIT < BN / 32) load_resid(p.epi, stg, col_base + (c + NSPLIT) * 32, lane, xn);
+    uint32_t raw[32];
+    tmem_ld_32x32(tmem_acc + ((quad * 32u) << 16) + c * 32, raw);
+    tmem_wait_ld();
+    epi_chunk(p.epi, p.N, ri, group, col_base + c * 32, c * 32, raw, lane, stg, x);
+    if (has_resid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = xn[i];
+    }
+  }
+  tc_fence_before();
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------ single-CTA kernel
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_WARPS1 = 4;
 
 template <int BN>
 struct TcCfg {
@@ -156,11 +247,13 @@ struct TcCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + BAR_BYTES + 1024;
+  static constexpr int STAGE_OFF = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + ((BAR_BYTES + 15) & ~15);
+  static constexpr int SMEM_BYTES = STAGE_OFF + EPI_WARPS1 * (int)sizeof(EpiStage) + 1024;
 };
 
+// Warp roles: 0-3 epilogue (TMEM lane quadrant = warp id), 4 TMA producer, 5 MMA issuer (+ TMEM allocation).
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -174,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  EpiStage* stages = reinterpret_cast<EpiStage*>(smem + Cfg::STAGE_OFF);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -188,11 +282,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], EPI_WARPS1);
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 5) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -201,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 128) {
     // ===================== TMA producer =====================
     int s = 0;
     uint32_t ph = 0;
@@ -222,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (threadIdx.x == 32) {
+  } else if (threadIdx.x == 160) {
     // ===================== MMA issuer (single thread) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     int s = 0;
@@ -253,28 +347,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) accph ^= 1;
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue warps: TMEM -> registers -> global =====================
-    const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+  } else if (warp < EPI_WARPS1) {
+    // ===================== epilogue warps =====================
     int acc = 0;
     uint32_t accph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
-      mbar_wait(&tfull[acc], accph);
-      tc_fence_after();
-      const int r = m_tile * BM + ew * 32 + lane;
-      const RowInfo ri = route_row(p.epi, p.M, r);
-      const int group = m_tile * 4 + ew;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((ew * 32u) << 16) + acc * BN + c * 32, raw);
-        tmem_wait_ld();
-        epi_chunk(p.epi, p.N, ri, group, n_tile * BN + c * 32, raw, lane);
-      }
-      tc_fence_before();
-      __syncwarp();
+      epilogue_tile<BN, 1>(p, stages[warp], tmem_base + acc * BN, warp, m_tile * BM + (int)warp * 32, n_tile * BN,
+                           lane, 0, &tfull[acc], accph);
       if (lane == 0) mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) accph ^= 1;
@@ -283,9 +364,143 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 5) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ CTA-pair kernel
+// cta_group::2 variant for the large GEMMs: a cluster of two CTAs (one SM pair) owns a 256 x 256 output tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 output columns), so the per-SM
+// fabric traffic per MMA cycle drops by a third compared with the single-CTA 128 x 256 tile (32 KB instead of 48 KB
+// per 64-deep k-block). The leader CTA's single MMA thread issues M=256 instructions that read both CTAs' shared
+// memory and write both CTAs' TMEM; commits are multicast to both CTAs' barriers.
+// Warp roles: 0-7 epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks), 8 TMA producer,
+// 9 MMA issuer (+ TMEM allocation). Eight epilogue warps double the thread-level parallelism that hides the
+// latencies of the per-chunk TMEM load / smem transpose / global access chain.
+constexpr int B2_STAGE_BYTES = 128 * BK * 2;  // half of a 256-column B tile
+constexpr int STAGES2 = 5;
+constexpr int EPI_WARPS2 = 8;
+constexpr int TC2_THREADS = (EPI_WARPS2 + 2) * 32;
+constexpr int TC2_BAR_BYTES = ((2 * STAGES2 + 4) * 8 + 16 + 15) & ~15;
+constexpr int TC2_STAGE_OFF = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + TC2_BAR_BYTES;
+constexpr int TC2_SMEM_BYTES = TC2_STAGE_OFF + EPI_WARPS2 * (int)sizeof(EpiStage) + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES2 * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES));
+  uint64_t* full = bars;                      // leader's copy is the live one (both CTAs' TMA bytes land there)
+  uint64_t* empty = bars + STAGES2;           // per CTA (multicast commit)
+  uint64_t* tfull = bars + 2 * STAGES2;       // per CTA (multicast commit)
+  uint64_t* tempty = bars + 2 * STAGES2 + 2;  // leader's copy: epilogue warps of both CTAs arrive on it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+  EpiStage* stages = reinterpret_cast<EpiStage*>(smem + TC2_STAGE_OFF);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-row tiles here
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 2 * EPI_WARPS2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == EPI_WARPS2 + 1) {
+    tmem_alloc_cg2(tmem_slot, 512);
+    tmem_relinquish_cg2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == EPI_WARPS2 * 32) {
+    // ===================== TMA producer (both CTAs; bytes are credited to the leader's barrier) =================
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (A_STAGE_BYTES + B2_STAGE_BYTES));
+        tma_load_2d_cg2(sA + s * A_STAGE_BYTES, &tmA, &full[s], kb * BK, m_tile * 256 + (int)rank * 128);
+        tma_load_2d_cg2(sB + s * B2_STAGE_BYTES, &tmB, &full[s], kb * BK, n_tile * BN + (int)rank * 128);
+        if (++s == STAGES2) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (threadIdx.x == (EPI_WARPS2 + 1) * 32 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
+      mbar_wait(&tempty[acc], accph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t da = umma_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES));
+        const uint64_t db = umma_desc_sw128(smem_u32(sB + s * B2_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit_cg2(&empty[s], 3);
+        if (++s == STAGES2) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+      umma_commit_cg2(&tfull[acc], 3);
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  } else if (warp < EPI_WARPS2) {
+    // ===================== epilogue warps (both CTAs, 128 rows each) =====================
+    const uint32_t quad = warp & 3;
+    const int split = (int)(warp >> 2);
+    int acc = 0;
+    uint32_t accph = 0;
+    for (int tile = cid; tile < total_tiles; tile += ncl) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      epilogue_tile<BN, 2>(p, stages[warp], tmem_base + acc * BN, quad,
+                           m_tile * 256 + (int)rank * 128 + (int)quad * 32, n_tile * BN, lane, split, &tfull[acc],
+                           accph);
+      if (lane == 0) mbar_arrive_cluster(&tempty[acc], 0);  // the leader's MMA thread owns accumulator reuse
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch its smem / TMEM
+  if (warp == EPI_WARPS2 + 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 512);
   }
 }
 
@@ -400,7 +615,7 @@ static PFN_encodeTiled get_encode_fn(std::string& err) {
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1 with row pitch `pitch_elems`; box = 64 x box_rows; 128B swizzle.
 int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsigned long long dim1,
-                        unsigned long long pitch_elems, unsigned box_rows, std::string& err) {
+                 unsigned long long pitch_elems, unsigned box_rows, std::string& err) {
   PFN_encodeTiled enc = get_encode_fn(err);
   if (!enc) return -1;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((pitch_elems * 2) & 15) != 0) {
@@ -452,13 +667,51 @@ static int launch_tc(const GemmOp& op, GemmParams& p, cudaStream_t stream, int n
   }
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int grid = total < num_sms ? total : num_sms;
-  gemm_tc_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("gemm_tc_kernel launch: ") + cudaGetErrorString(ce);
     return -1;
   }
   return 0;
+}
+
+static int launch_tc2(const GemmOp& op, GemmParams& p, cudaStream_t stream, int num_sms, std::string& err) {
+  CUtensorMap tmA, tmB;
+  if (make_tmap_2d(&tmA, op.A, (unsigned long long)op.K, (unsigned long long)op.a_rows, (unsigned long long)op.lda,
+                   128, err))
+    return -1;
+  if (make_tmap_2d(&tmB, op.W, (unsigned long long)op.K, (unsigned long long)op.N, (unsigned long long)op.K, 128,
+                   err))
+    return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES);
+    if (ce != cudaSuccess) {
+      err = std::string("cudaFuncSetAttribute(gemm_tc2_kernel): ") + cudaGetErrorString(ce);
+      return -1;
+    }
+    attr_set = true;
+  }
+  const int total = p.num_m_tiles * p.num_n_tiles;
+  const int max_clusters = num_sms / 2;
+  const int grid = 2 * (total < max_clusters ? total : max_clusters);
+  gemm_tc2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    err = std::string("gemm_tc2_kernel launch: ") + cudaGetErrorString(ce);
+    return -1;
+  }
+  return 0;
+}
+
+static bool force_single_cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_GEMM_1CTA");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err) {
@@ -517,6 +770,11 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, s
   if (op.a_mode == 1) {
     p.num_n_tiles = op.N / 64;
     return launch_tc<64>(op, p, stream, num_sms, err);
+  }
+  if (op.N % 256 == 0 && !force_single_cta()) {
+    p.num_m_tiles = ceil_div(op.M, 256);
+    p.num_n_tiles = op.N / 256;
+    return launch_tc2(op, p, stream, num_sms, err);
   }
   if (op.N % 256 == 0) {
     p.num_n_tiles = op.N / 256;

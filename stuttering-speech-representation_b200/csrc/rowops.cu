@@ -72,7 +72,7 @@ layernorm_kernel(const LayerNormArgs a) {
     v[i][3] = (v[i][3] - mean) * rstd * g.w + b.w;
     if (a.gelu) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = gelu_erf_r(v[i][j]);
+      for (int j = 0; j < 4; ++j) v[i][j] = gelu_fast(v[i][j]);
     }
   }
   if (a.out_f32 != nullptr) {
