@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_kernels_gpu.py -q -k "attention" -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python tools/attn_probe.py
