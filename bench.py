@@ -190,11 +190,17 @@ def roofline_from_profile(prof: dict, peaks: dict) -> tuple[dict, dict]:
     total_ms = sum(v["ms"] for v in prof.values())
     ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     peak = peaks["bf16_sustained"] or 1400.0
-    roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all launches of one step)",
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("traffic_bytes_per_launch_avg")
+    roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 bf16 GEMM, all launches of one step)",
             "achieved": round(ach, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
             "peak_source": peaks["source"] + ", sustained bf16", "launches_per_step": n,
             "avg_launch_ms": round(ms / max(n, 1), 4), "share_of_step": round(ms / max(total_ms, 1e-9), 4),
-            "traffic": None}
+            "traffic": traffic,
+            "traffic_note": "dram read+write bytes per launch, ncu --set full average over one layer's four GEMMs "
+                            "(profiles/r01_gemm_traffic.json)" if traffic else None}
     kern = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                 "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1) if v["flops"] else None}
             for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
