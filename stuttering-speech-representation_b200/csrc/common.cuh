@@ -63,18 +63,20 @@ int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsi
 // erf-GELU with erfc(|z|) from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 / fp32-residual
 // noise floor of the consumers) : 2 MUFU ops + ~10 FMA instead of libdevice erff's two-branch polynomial.
 //   gelu(x) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt(2))
+// Constants are pre-folded (1/sqrt(2) into p and into the exponent scale, 1/2 into the polynomial) so that the whole
+// function is 13 instructions: FFMA, MUFU.RCP, 4 FFMA, 4 FMUL, MUFU.EX2, FMNMX, FFMA.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float ax = fabsf(x);
-  const float z = ax * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float pl = fmaf(1.061405429f, t, -1.453152027f);
-  pl = fmaf(pl, t, 1.421413741f);
-  pl = fmaf(pl, t, -0.284496736f);
-  pl = fmaf(pl, t, 0.254829592f);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
+  float pl = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  pl = fmaf(pl, t, 0.5f * 1.421413741f);
+  pl = fmaf(pl, t, 0.5f * -0.284496736f);
+  pl = fmaf(pl, t, 0.5f * 0.254829592f);
   float ex;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));
-  const float q = pl * t * ex;  // erfc(z)
-  return fmaxf(x, 0.0f) - 0.5f * ax * q;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((ax * -0.5f * 1.4426950408889634f) * ax));  // exp(-x^2/2)
+  const float w = (pl * t) * ax;                // 0.5 |x| erfc(z) / exp(-z^2)
+  return fmaf(-w, ex, fmaxf(x, 0.0f));
 }
 
 #endif

@@ -257,8 +257,10 @@ __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Declared 1024-byte aligned (128B-swizzle atoms) and used directly, so that the compiler keeps every access in the
+  // shared address space (LDS/STS); an integer round-trip to align the base would demote them to generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + Cfg::B_STAGE_BYTES));
@@ -391,8 +393,10 @@ constexpr int TC2_SMEM_BYTES = TC2_STAGE_OFF + EPI_WARPS2 * (int)sizeof(EpiStage
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr int BN = 256;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Declared 1024-byte aligned (128B-swizzle atoms) and used directly, so that the compiler keeps every access in the
+  // shared address space (LDS/STS); an integer round-trip to align the base would demote them to generic LD/ST.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES2 * A_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES));
