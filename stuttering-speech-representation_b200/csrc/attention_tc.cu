@@ -1,19 +1,22 @@
 // Flash-style multi-head self-attention on the 5th-gen tensor cores (sm_100a), head_dim 64.
 //
 // Persistent, warp-specialised kernel; a work item is one (clip, head, 128-query tile); each item loops over
-// 128-key blocks:
-//     warp 4      TMA producer: Q per item, K_j / V_j tiles through a 2-stage ring that runs ahead across items,
+// 64-key blocks. Everything is double buffered so that the softmax warps never wait for a tensor-core round trip
+// in steady state:
+//     warp 4      TMA producer: Q per item, K_j / V_j tiles through a 4-stage ring that runs ahead across items,
 //                 all straight out of the fused qkv activation matrix (no head split / transpose pass)
-//     warp 5      single-thread tcgen05.mma issuer:  S = Q K_j^T  -> TMEM[0,128) ;  PV_j = P_j V_j -> TMEM[128,192)
+//     warp 5      single-thread tcgen05.mma issuer. S_{n+1} = Q K^T is issued BEFORE PV_n, so the next block's scores
+//                 are computed while the softmax warps work on the current one:
+//                     S_n  -> TMEM S[n&1] (64 columns) ;  PV_n = P_n V_n -> TMEM O[n&1] (64 columns)
 //                 (driver warps carry the highest warp ids: the sub-partition arbiter favours them)
 //     warps 0-3   softmax: thread = query row (TMEM lane). tcgen05.ld S, + gated relative-position bias, key mask,
-//                 online max / sum in fp32, P (bf16) written to shared memory in the UMMA 128B-swizzled K-major
-//                 layout; after PV_j completes the partial product is folded into the fp32 O accumulator kept in
-//                 registers (so no TMEM read-modify-write is needed for the online-softmax rescale).
-//   Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each): while one runs its softmax on the CUDA
-//   cores the other owns the tensor pipe. Padding is not computed: the last key block uses an MMA N / K extent
-//   rounded to 16 live keys, softmax touches only the 32-column chunks that hold live keys, and warps whose 32 query
-//   rows are all beyond the clip's length only keep the barrier protocol going.
+//                 online max / sum in fp32, P (bf16) -> shared memory P[n&1] in the UMMA 128B-swizzled K-major layout.
+//                 PV_{n-1} is folded into the fp32 O accumulator (registers) one block LATE, i.e. after P_n has been
+//                 handed to the tensor core, by which time it has long completed; no TMEM read-modify-write is
+//                 needed for the online-softmax rescale.
+//   Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each). Padding is not computed: the last key
+//   block uses an MMA N / K extent rounded to 16 live keys, softmax touches only the 32-column chunks that hold live
+//   keys, and warps whose 32 query rows are all beyond the clip's length only keep the barrier protocol going.
 //
 // Reference arithmetic: see attention.cu (same math; that mma.sync kernel is kept as a cross-check).
 #include "common.cuh"
@@ -26,17 +29,20 @@ using namespace ptx;
 
 namespace {
 
-constexpr int QT = 128;    // queries per item
-constexpr int KBLK = 128;  // keys per block
+constexpr int QT = 128;   // queries per item
+constexpr int KBLK = 64;  // keys per block
 constexpr int HD = 64;
-constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 tile = 16 KB
+constexpr int KV_STAGES = 4;
+constexpr int Q_BYTES = 128 * 64 * 2;   // [128 x 64] bf16
+constexpr int KV_BYTES = 64 * 64 * 2;   // [64 x 64] bf16 (K or V of one block)
+constexpr int P_BYTES = 128 * 64 * 2;   // [128 q x 64 keys] bf16
 constexpr int SM_Q = 0;
-constexpr int SM_KV = TILE_BYTES;             // 2 stages x (K, V)
-constexpr int SM_P = SM_KV + 4 * TILE_BYTES;  // [128 x 128] bf16 as two K-major sub-tiles
-constexpr int SM_BAR = SM_P + 2 * TILE_BYTES;
-constexpr int ATT_SMEM = SM_BAR + 128;
+constexpr int SM_KV = Q_BYTES;                               // KV_STAGES x (K, V)
+constexpr int SM_P = SM_KV + KV_STAGES * 2 * KV_BYTES;       // 2 buffers
+constexpr int SM_BAR = SM_P + 2 * P_BYTES;
+constexpr int ATT_SMEM = SM_BAR + 256;
 constexpr int TMEM_COLS = 256;
-constexpr int TM_S = 0, TM_O = 128;
+constexpr int TM_S = 0, TM_O = 128;  // S[2] at columns 0 / 64, O[2] at columns 128 / 192
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -77,33 +83,75 @@ __device__ __forceinline__ Item decode_item(const AttentionArgs& a, int idx) {
   return it;
 }
 
+constexpr float LAZY_T = 8.0f;
+
+// One 32-key chunk of one query row: scores (+ gated relative-position bias, + key mask) -> running block max and,
+// if WRITE_P, probabilities exp(s - ref) accumulated into l_blk and stored as bf16 into the row's P tile columns
+// col0 .. col0+3 (16-byte units, XOR-swizzled by row % 8 = the UMMA / TMA 128B swizzle).
+template <bool HAS_BIAS, bool MASK, bool WRITE_P>
+__device__ __forceinline__ void chunk(const uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel,
+                                      float mu2, float& m_blk, float& l_blk, uint8_t* prow, uint32_t col0) {
+  uint32_t packed[16];
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) {
+    float v0 = __uint_as_float(raw[k]), v1 = __uint_as_float(raw[k + 1]);
+    if (HAS_BIAS) {
+      v0 = fmaf(gate, __ldg(rel + jg0 + k), v0);
+      v1 = fmaf(gate, __ldg(rel + jg0 + k + 1), v1);
+    }
+    if (MASK) {
+      if (jg0 + k >= len) v0 = -INFINITY;
+      if (jg0 + k + 1 >= len) v1 = -INFINITY;
+    }
+    m_blk = fmaxf(m_blk, fmaxf(v0, v1));
+    if (WRITE_P) {
+      const float p0 = ex2_approx(fmaf(v0, LOG2E, -mu2));
+      const float p1 = ex2_approx(fmaf(v1, LOG2E, -mu2));
+      l_blk += p0 + p1;
+      __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+      packed[k >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+  }
+  if (WRITE_P) {
+    const uint32_t sw = (uint32_t)((reinterpret_cast<uintptr_t>(prow) >> 7) & 7);  // row % 8 (rows are 128 B apart)
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(prow + ((col0 + q) ^ sw) * 16) =
+          make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+  }
+}
+
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(192, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs a, const int n_items) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
+                    const AttentionArgs a, const int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;   // [2]
-  uint64_t* kv_empty = bars + 4;  // [2]
-  uint64_t* bar_s = bars + 6;
-  uint64_t* bar_p = bars + 7;
-  uint64_t* bar_o = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars + 2;               // [KV_STAGES]
+  uint64_t* kv_empty = bars + 2 + KV_STAGES;  // [KV_STAGES]
+  uint64_t* bar_s = bars + 2 + 2 * KV_STAGES;  // [2]
+  uint64_t* bar_p = bar_s + 2;                 // [2]
+  uint64_t* bar_o = bar_p + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 2);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) __trap();
-    prefetch_tmap(&tm);
+    prefetch_tmap(&tmq);
+    prefetch_tmap(&tmkv);
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 4);
+      mbar_init(&bar_o[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 5) {
@@ -117,23 +165,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
 
   if (threadIdx.x == 128) {
     // ============================ TMA producer ============================
-    uint32_t n_item = 0, n_kv = 0;
+    uint32_t n_item = 0, n = 0;
     Item nxt = decode_item(a, blockIdx.x);
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
       const Item it = nxt;
-      // the next item's length load is issued now and consumed one iteration later (keeps it off the critical path)
-      if (idx + (int)gridDim.x < n_items) nxt = decode_item(a, idx + gridDim.x);
+      if (idx + (int)gridDim.x < n_items) nxt = decode_item(a, idx + gridDim.x);  // prefetch the length load
       if (!it.valid) continue;
       const int row0 = it.b * a.slot;
       mbar_wait(q_empty, (n_item & 1) ^ 1);
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(smem + SM_Q, &tm, q_full, it.h * HD, row0 + it.q0);
-      for (int j = 0; j < it.nkb; ++j, ++n_kv) {
-        const int s = n_kv & 1;
-        mbar_wait(&kv_empty[s], ((n_kv >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-        tma_load_2d(smem + SM_KV + s * 2 * TILE_BYTES, &tm, &kv_full[s], a.D + it.h * HD, row0 + j * KBLK);
-        tma_load_2d(smem + SM_KV + s * 2 * TILE_BYTES + TILE_BYTES, &tm, &kv_full[s], 2 * a.D + it.h * HD,
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(smem + SM_Q, &tmq, q_full, it.h * HD, row0 + it.q0);
+      for (int j = 0; j < it.nkb; ++j, ++n) {
+        const int s = n % KV_STAGES;
+        mbar_wait(&kv_empty[s], ((n / KV_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
+        tma_load_2d(smem + SM_KV + s * 2 * KV_BYTES, &tmkv, &kv_full[s], a.D + it.h * HD, row0 + j * KBLK);
+        tma_load_2d(smem + SM_KV + s * 2 * KV_BYTES + KV_BYTES, &tmkv, &kv_full[s], 2 * a.D + it.h * HD,
                     row0 + j * KBLK);
       }
       ++n_item;
@@ -142,48 +189,56 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
     // ============================ MMA issuer ============================
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
     const uint64_t dq = umma_desc_sw128(smem_u32(smem + SM_Q));
-    const uint64_t dp0 = umma_desc_sw128(smem_u32(smem + SM_P));
-    const uint64_t dp1 = umma_desc_sw128(smem_u32(smem + SM_P + TILE_BYTES));
-    uint32_t n_item = 0, n_kv = 0;
+    uint32_t n_item = 0, n = 0;
+    bool have_prev = false;
+    int prev_n16 = 0;
+    // PV of block n-1 is issued after S of block n
+    auto issue_pv_prev = [&]() {
+      const uint32_t pn = n - 1;
+      const int ps = pn % KV_STAGES;
+      mbar_wait(&bar_p[pn & 1], (pn >> 1) & 1);  // P_{n-1} is in shared memory, O[(n-1)&1] has been folded
+      tc_fence_after();
+      const uint64_t dp = umma_desc_sw128(smem_u32(smem + SM_P + (pn & 1) * P_BYTES));
+      const uint64_t dv = umma_desc_sw128_mn(smem_u32(smem + SM_KV + ps * 2 * KV_BYTES + KV_BYTES));
+      for (int k = 0; k < prev_n16; ++k)  // 16 keys per MMA: P advances 32 B, V two 8-row groups = 2048 B
+        umma_bf16(tmem + TM_O + (pn & 1) * 64, dp + 2 * k, dv + (uint64_t)(k * 2048 >> 4), idesc_pv, k != 0);
+      umma_commit(&kv_empty[ps]);
+      umma_commit(&bar_o[pn & 1]);
+    };
     Item nxt = decode_item(a, blockIdx.x);
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
       const Item it = nxt;
       if (idx + (int)gridDim.x < n_items) nxt = decode_item(a, idx + gridDim.x);
       if (!it.valid) continue;
       mbar_wait(q_full, n_item & 1);
-      for (int j = 0; j < it.nkb; ++j, ++n_kv) {
-        const int s = n_kv & 1;
+      for (int j = 0; j < it.nkb; ++j) {
+        const int s = n % KV_STAGES;
         const int nlive = min(KBLK, it.len - j * KBLK);
         const int n16 = (nlive + 15) >> 4;  // live keys in units of 16
-        mbar_wait(&kv_full[s], (n_kv >> 1) & 1);
+        mbar_wait(&kv_full[s], (n / KV_STAGES) & 1);
         tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(smem + SM_KV + s * 2 * TILE_BYTES));
-        const uint64_t dv = umma_desc_sw128_mn(smem_u32(smem + SM_KV + s * 2 * TILE_BYTES + TILE_BYTES));
+        const uint64_t dk = umma_desc_sw128(smem_u32(smem + SM_KV + s * 2 * KV_BYTES));
         const uint32_t idesc_s = umma_idesc_bf16(128, n16 * 16);
+        // S[n&1] was last read by the softmax of block n-2, which finished before bar_p of block n-2 (waited below)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + TM_S + (n & 1) * 64, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
         if (j == it.nkb - 1) umma_commit(q_empty);  // Q tile may be overwritten once these MMAs retire
-        umma_commit(bar_s);
-        mbar_wait(bar_p, n_kv & 1);  // P_j is in shared memory (and O_{j-1} has been read back)
-        tc_fence_after();
-        for (int k = 0; k < n16; ++k) {
-          const uint64_t dp = (k < 4 ? dp0 : dp1) + 2 * (k & 3);
-          // V: 16 keys per MMA = two 8-row groups = 2048 bytes
-          umma_bf16(tmem + TM_O, dp, dv + (uint64_t)(k * 2048 >> 4), idesc_pv, k != 0);
-        }
-        umma_commit(&kv_empty[s]);
-        umma_commit(bar_o);
+        umma_commit(&bar_s[n & 1]);
+        if (have_prev) issue_pv_prev();
+        have_prev = true;
+        prev_n16 = n16;
+        ++n;
       }
       ++n_item;
     }
+    if (have_prev) issue_pv_prev();
   } else if (warp < 4) {
     // ============================ softmax / output warps ============================
     const uint32_t quad = warp;  // TMEM lane quadrant accessible to this warp
     const int il = quad * 32 + lane;
     const uint32_t lane_addr = (quad * 32u) << 16;
-    uint8_t* prow = smem + SM_P + il * 128;
     const uint32_t sw = il & 7;
-    uint32_t n_kv = 0;
+    uint32_t n = 0;
     Item nxt = decode_item(a, blockIdx.x);
     float gate_nxt = 0.f;
     if (HAS_BIAS && nxt.q0 + il < a.slot)
@@ -199,81 +254,128 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
       }
       if (!it.valid) continue;
       const int row0 = it.b * a.slot;
-      const int i = it.q0 + il;                                   // query index inside the clip
-      const bool warp_live = it.q0 + (int)quad * 32 < it.len;      // at least one live query row in this warp
+      const int i = it.q0 + il;                                // query index inside the clip
+      const bool warp_live = it.q0 + (int)quad * 32 < it.len;   // at least one live query row in this warp
       const float* rel = nullptr;
       if (HAS_BIAS) rel = a.relbias + (long long)it.h * a.rel_stride + a.rel_center - i;  // rel[j] = table[h][j - i]
       float o[64];
 #pragma unroll
       for (int d = 0; d < 64; ++d) o[d] = 0.f;
       float m_run = -INFINITY, l_run = 0.f;
+      float alpha_pend = 1.f;  // rescale that goes with the not-yet-folded PV of the previous block
 
-      for (int j = 0; j < it.nkb; ++j, ++n_kv) {
+      // fold PV of block `pn` (already relative to the running max at that block) into the accumulator
+      auto fold = [&](uint32_t pn, float alpha) {
+        mbar_wait(&bar_o[pn & 1], (pn >> 1) & 1);
+        __syncwarp();
+        tc_fence_after();
+        if (warp_live) {
+          uint32_t r0[32], r1[32];  // both halves in flight before the single wait
+          tmem_ld_32x32(tmem + lane_addr + TM_O + (pn & 1) * 64, r0);
+          tmem_ld_32x32(tmem + lane_addr + TM_O + (pn & 1) * 64 + 32, r1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[k] = fmaf(o[k], alpha, __uint_as_float(r0[k]));
+#pragma unroll
+          for (int k = 0; k < 32; ++k) o[32 + k] = fmaf(o[32 + k], alpha, __uint_as_float(r1[k]));
+        }
+        tc_fence_before();
+      };
+
+      for (int j = 0; j < it.nkb; ++j, ++n) {
         const int k0 = j * KBLK;
         const int nlive = min(KBLK, it.len - k0);
-        const int nch = (nlive + 31) >> 5;  // 32-column chunks that hold live keys
+        const int nch = (nlive + 31) >> 5;  // 32-column chunks that hold live keys (1 or 2)
         const bool need_mask = (nlive & 31) != 0;
-        mbar_wait(bar_s, n_kv & 1);
+        const uint32_t ts = tmem + lane_addr + TM_S + (n & 1) * 64;
+        uint8_t* prow = smem + SM_P + (n & 1) * P_BYTES + il * 128;
+        mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
         __syncwarp();
         tc_fence_after();
         float alpha = 1.f;
-        if (warp_live) {
-          // ---- pass 1: block row maximum ----
-          float m_blk = -INFINITY;
-#pragma unroll 1
+        if (warp_live && HAS_BIAS) {
+          // Short sequences with the gated bias (WavLM): classic two-pass online softmax per block (measured faster
+          // than the lazy variant for 2-3 blocks per item).
+          float m_blk = -INFINITY, l_blk = 0.f, unused = 0.f;
           for (int c = 0; c < nch; ++c) {
             uint32_t raw[32];
-            tmem_ld_32x32(tmem + lane_addr + TM_S + c * 32, raw);
+            tmem_ld_32x32(ts + c * 32, raw);
             tmem_wait_ld();
-            const bool mask_here = need_mask && (c == nch - 1);
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              float v = __uint_as_float(raw[k]);
-              const int jg = k0 + c * 32 + k;
-              if (HAS_BIAS) v = fmaf(gate, __ldg(rel + jg), v);
-              if (mask_here && jg >= it.len) v = -INFINITY;
-              m_blk = fmaxf(m_blk, v);
-            }
+            if (need_mask && c == nch - 1)
+              chunk<HAS_BIAS, true, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, unused, nullptr, 0);
+            else
+              chunk<HAS_BIAS, false, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, unused, nullptr, 0);
           }
           const float m_new = fmaxf(m_run, m_blk);
           const float mu = (m_new == -INFINITY) ? 0.f : m_new;
           alpha = ex2_approx((m_run - mu) * LOG2E);
           const float mu2 = mu * LOG2E;
           m_run = m_new;
-          // ---- pass 2: probabilities -> bf16 P tile in shared memory (128B-swizzled K-major) ----
-          float l_blk = 0.f;
-#pragma unroll 1
+          float dummy = -INFINITY;
           for (int c = 0; c < nch; ++c) {
             uint32_t raw[32];
-            tmem_ld_32x32(tmem + lane_addr + TM_S + c * 32, raw);
+            tmem_ld_32x32(ts + c * 32, raw);
             tmem_wait_ld();
-            const bool mask_here = need_mask && (c == nch - 1);
-            uint32_t packed[16];
-#pragma unroll
-            for (int k = 0; k < 32; k += 2) {
-              float v0 = __uint_as_float(raw[k]), v1 = __uint_as_float(raw[k + 1]);
-              const int jg = k0 + c * 32 + k;
-              if (HAS_BIAS) {
-                v0 = fmaf(gate, __ldg(rel + jg), v0);
-                v1 = fmaf(gate, __ldg(rel + jg + 1), v1);
-              }
-              if (mask_here) {
-                if (jg >= it.len) v0 = -INFINITY;
-                if (jg + 1 >= it.len) v1 = -INFINITY;
-              }
-              const float p0 = ex2_approx(fmaf(v0, LOG2E, -mu2));
-              const float p1 = ex2_approx(fmaf(v1, LOG2E, -mu2));
-              l_blk += p0 + p1;
-              __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-              packed[k >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+            if (need_mask && c == nch - 1)
+              chunk<HAS_BIAS, true, true>(raw, k0 + c * 32, it.len, gate, rel, mu2, dummy, l_blk, prow, c * 4);
+            else
+              chunk<HAS_BIAS, false, true>(raw, k0 + c * 32, it.len, gate, rel, mu2, dummy, l_blk, prow, c * 4);
+          }
+          l_run = l_run * alpha + l_blk;
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        } else if (warp_live) {
+          float m_blk = -INFINITY, l_blk = 0.f;
+          if (j == 0) {
+            // first block of the item: exact row maximum first (nothing to rescale yet)
+            for (int c = 0; c < nch; ++c) {
+              uint32_t raw[32];
+              tmem_ld_32x32(ts + c * 32, raw);
+              tmem_wait_ld();
+              if (need_mask && c == nch - 1)
+                chunk<HAS_BIAS, true, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
+              else
+                chunk<HAS_BIAS, false, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
             }
-            // chunk c covers keys [c*32, c*32+32): sub-tile c/2, 16-byte columns (c%2)*4 .. +3, XOR-swizzled by row%8
-            uint8_t* sub = prow + (c >> 1) * TILE_BYTES;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t col = ((c & 1) * 4 + q) ^ sw;
-              *reinterpret_cast<uint4*>(sub + col * 16) =
-                  make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            m_run = m_blk;
+          }
+          // probabilities relative to the running reference max m_run (possibly stale: see below)
+          float mu2 = ((m_run == -INFINITY) ? 0.f : m_run) * LOG2E;
+          if (nch == 2) {
+            uint32_t r0[32], r1[32];  // both chunks in flight before the single wait
+            tmem_ld_32x32(ts, r0);
+            tmem_ld_32x32(ts + 32, r1);
+            tmem_wait_ld();
+            chunk<HAS_BIAS, false, true>(r0, k0, it.len, gate, rel, mu2, m_blk, l_blk, prow, 0);
+            if (need_mask)
+              chunk<HAS_BIAS, true, true>(r1, k0 + 32, it.len, gate, rel, mu2, m_blk, l_blk, prow, 4);
+            else
+              chunk<HAS_BIAS, false, true>(r1, k0 + 32, it.len, gate, rel, mu2, m_blk, l_blk, prow, 4);
+          } else {
+            uint32_t raw[32];
+            tmem_ld_32x32(ts, raw);
+            tmem_wait_ld();
+            if (need_mask)
+              chunk<HAS_BIAS, true, true>(raw, k0, it.len, gate, rel, mu2, m_blk, l_blk, prow, 0);
+            else
+              chunk<HAS_BIAS, false, true>(raw, k0, it.len, gate, rel, mu2, m_blk, l_blk, prow, 0);
+          }
+          // Lazy online softmax: later blocks keep the reference max unless the block maximum exceeds it by more
+          // than LAZY_T (probabilities then stay below e^LAZY_T, harmless in bf16 / fp32); only then is the block
+          // redone against the new maximum and the accumulated state rescaled. Any shift is mathematically exact.
+          const bool redo = (j > 0) && (m_blk > m_run + LAZY_T);
+          if (__any_sync(0xffffffffu, redo)) {
+            if (redo) {
+              alpha = ex2_approx((m_run - m_blk) * LOG2E);
+              m_run = m_blk;
+            }
+            mu2 = ((m_run == -INFINITY) ? 0.f : m_run) * LOG2E;
+            l_blk = 0.f;
+            float dummy = -INFINITY;
+            for (int c = 0; c < nch; ++c) {
+              uint32_t raw[32];
+              tmem_ld_32x32(ts + c * 32, raw);
+              tmem_wait_ld();
+              chunk<HAS_BIAS, true, true>(raw, k0 + c * 32, it.len, gate, rel, mu2, dummy, l_blk, prow, c * 4);
             }
           }
           l_run = l_run * alpha + l_blk;
@@ -281,23 +383,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm, const AttentionArgs 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-        // ---- fold PV_j into the register accumulator ----
-        mbar_wait(bar_o, n_kv & 1);
-        __syncwarp();
-        tc_fence_after();
-        if (warp_live) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, raw);
-            tmem_wait_ld();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) o[c * 32 + k] = fmaf(o[c * 32 + k], alpha, __uint_as_float(raw[k]));
-          }
-        }
-        tc_fence_before();
+        if (lane == 0) mbar_arrive(&bar_p[n & 1]);
+        // ---- late fold: PV of the previous block of this item completed while this block's softmax ran ----
+        if (j > 0) fold(n - 1, alpha_pend);
+        alpha_pend = alpha;
       }
+      fold(n - 1, alpha_pend);  // last block of the item: the one true round-trip wait per item
       // ---- normalise and store this row (rows at or beyond the clip length are never read downstream) ----
       if (i < it.len) {
         const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
@@ -333,8 +424,9 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
     return -1;
   }
   if (a.B <= 0 || a.slot <= 0) return 0;
-  CUtensorMap tm;
-  if (make_tmap_2d(&tm, a.qkv, 3ULL * a.D, (unsigned long long)a.B * a.slot, 3ULL * a.D, 128, err)) return -1;
+  CUtensorMap tmq, tmkv;
+  if (make_tmap_2d(&tmq, a.qkv, 3ULL * a.D, (unsigned long long)a.B * a.slot, 3ULL * a.D, QT, err)) return -1;
+  if (make_tmap_2d(&tmkv, a.qkv, 3ULL * a.D, (unsigned long long)a.B * a.slot, 3ULL * a.D, KBLK, err)) return -1;
   static bool attr_set = false;
   static int num_sms = 148;
   if (!attr_set) {
@@ -359,9 +451,9 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   }
   const int grid = (int)(items < 2LL * num_sms ? items : 2LL * num_sms);
   if (a.gate != nullptr)
-    attention_tc_kernel<true><<<grid, 192, ATT_SMEM, st>>>(tm, a, (int)items);
+    attention_tc_kernel<true><<<grid, 192, ATT_SMEM, st>>>(tmq, tmkv, a, (int)items);
   else
-    attention_tc_kernel<false><<<grid, 192, ATT_SMEM, st>>>(tm, a, (int)items);
+    attention_tc_kernel<false><<<grid, 192, ATT_SMEM, st>>>(tmq, tmkv, a, (int)items);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("attention_tc launch: ") + cudaGetErrorString(ce);
