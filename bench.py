@@ -366,8 +366,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "WavLM-Large (24 layers, d=1024) per-layer pooled embeddings, 3 s clips "
-                                   f"(bounded sample: {n} clips per step on host cores)"},
+            "config": {"workload": "WavLM-Large (24 layers, d=1024) per-layer pooled embeddings, 3 s clips, "
+                                   f"batch {args.batch} per GPU (BASELINE configs[1])",
+                       "clip_samples": 48000, "weights": "seeded random init (seed 0)",
+                       "reference_sample": f"{n} clips of that workload per step, one clip per HF forward on the "
+                                           "host cores (the reference's own loop, REF/WavLM_embeddings.py:583-594)"},
             "cpu_baseline": cb,
             "e2e": {"value": round(value, 3), "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -246,3 +246,69 @@ def test_dropin_signatures_and_error_convention():
     out = ssr_b200.extract_embeddings_from_audio_whisper(clip, enc, wfe, "cuda", names)
     assert list(out.keys()) == ["encoder_layer_2", "encoder_layer_1"]
     assert out["encoder_layer_2"].shape == (256,)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_wavlm_long_and_ragged_clips_vs_oracle():
+    """10 s clip (T=499: multi-block attention with the relative-position bias, bucket table past +-80) batched with
+    short ones; the minimum-length clip (400 samples -> 1 frame); empty batch."""
+    from oracle.wavlm_oracle import WavLMOracle
+    from ssr_b200 import synth
+
+    model, fe, eng = wavlm("tiny_stable")
+    clips = [synth.noise_clips(1, 160000, seed=21)[0], synth.noise_clips(1, 400, seed=22)[0],
+             synth.tonal_clip(70001), synth.noise_clips(1, 16000, seed=23)[0]]
+    assert [eng.num_frames(len(c)) for c in clips] == [499, 1, 218, 49]
+    orc = WavLMOracle.from_hf(model)
+    ref = np.stack([orc.pooled(c, fe.do_normalize) for c in clips])
+    got = eng.pooled(clips)
+    check_pooled(got, ref, "wavlm tiny_stable long+ragged")
+    assert eng.pooled([]).shape == (0, 4, 512)
+
+
+def test_wavlm_post_ln_long_clip_vs_oracle():
+    from oracle.wavlm_oracle import WavLMOracle
+    from ssr_b200 import synth
+
+    model, fe, eng = wavlm("tiny_post")
+    clips = [synth.noise_clips(1, 100000, seed=31)[0], synth.noise_clips(1, 48000, seed=32)[0]]
+    orc = WavLMOracle.from_hf(model)
+    ref = np.stack([orc.pooled(c, fe.do_normalize) for c in clips])
+    check_pooled(eng.pooled(clips), ref, "wavlm tiny_post long")
+
+
+def test_whisper_truncates_past_30s_and_full_batch_properties():
+    """HF truncates to 480 000 samples (feature_extraction_whisper.py:296-303); BASELINE config 2 batch (64 clips):
+    run-to-run bit-identical and batch-neighbour independent."""
+    from ssr_b200 import synth
+
+    _, _, teng = whisper("tiny")
+    long = synth.noise_clips(1, 500000, seed=41)[0]
+    a = teng.pooled([long])
+    b = teng.pooled([long[:480000]])
+    assert np.array_equal(a, b)
+
+    _, _, eng = whisper("large")
+    clips = [synth.clip_by_index(i) for i in range(64)]
+    x = eng.pooled(clips)
+    y = eng.pooled(clips)
+    assert np.isfinite(x).all() and np.array_equal(x, y)
+    alone = eng.pooled([clips[5]])
+    np.testing.assert_allclose(alone[0], x[5], rtol=0, atol=2e-6 * np.abs(x).max())
+
+
+def test_batch_shims_match_per_clip_shims():
+    import ssr_b200
+    from ssr_b200 import synth
+    from ssr_b200.extract import extract_wavlm_embeddings_batch
+
+    model, fe, _ = wavlm("tiny_post")
+    clips = synth.mixed_clips()[:3]
+    idx = [2, 1, 0]
+    batch = extract_wavlm_embeddings_batch(clips, model, fe, "cuda:0", idx)
+    assert len(batch) == 3
+    for c, d in zip(clips, batch):
+        one = ssr_b200.extract_embeddings_from_audio_wavlm(c, model, fe, "cuda:0", idx)
+        assert list(one) == list(d) == ["layer_2", "layer_1", "layer_0"]
+        for k in one:
+            np.testing.assert_allclose(one[k], d[k], rtol=0, atol=2e-6 * max(1.0, np.abs(d[k]).max()))
