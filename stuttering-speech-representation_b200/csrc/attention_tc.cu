@@ -296,16 +296,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         if (warp_live && HAS_BIAS) {
           // Short sequences with the gated bias (WavLM): classic two-pass online softmax per block (measured faster
           // than the lazy variant for 2-3 blocks per item).
-          float m_blk = -INFINITY, l_blk = 0.f, unused = 0.f;
+          // Pass 1 adds the bias / mask, takes the row maximum and writes the biased scores back to TMEM, so pass 2
+          // does not touch the bias table again.
+          float m_blk = -INFINITY, l_blk = 0.f;
           for (int c = 0; c < nch; ++c) {
             uint32_t raw[32];
             tmem_ld_32x32(ts + c * 32, raw);
             tmem_wait_ld();
-            if (need_mask && c == nch - 1)
-              chunk<HAS_BIAS, true, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, unused, nullptr, 0);
-            else
-              chunk<HAS_BIAS, false, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, unused, nullptr, 0);
+            const int jg0 = k0 + c * 32;
+            const bool mask_here = need_mask && c == nch - 1;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              float v = fmaf(gate, __ldg(rel + jg0 + k), __uint_as_float(raw[k]));
+              if (mask_here && jg0 + k >= it.len) v = -INFINITY;
+              m_blk = fmaxf(m_blk, v);
+              raw[k] = __float_as_uint(v);
+            }
+            tmem_st_32x32(ts + c * 32, raw);
           }
+          tmem_wait_st();
           const float m_new = fmaxf(m_run, m_blk);
           const float mu = (m_new == -INFINITY) ? 0.f : m_new;
           alpha = ex2_approx((m_run - mu) * LOG2E);
@@ -316,10 +325,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             uint32_t raw[32];
             tmem_ld_32x32(ts + c * 32, raw);
             tmem_wait_ld();
-            if (need_mask && c == nch - 1)
-              chunk<HAS_BIAS, true, true>(raw, k0 + c * 32, it.len, gate, rel, mu2, dummy, l_blk, prow, c * 4);
-            else
-              chunk<HAS_BIAS, false, true>(raw, k0 + c * 32, it.len, gate, rel, mu2, dummy, l_blk, prow, c * 4);
+            chunk<false, false, true>(raw, k0 + c * 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, c * 4);
           }
           l_run = l_run * alpha + l_blk;
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
