@@ -52,8 +52,20 @@ struct GemmOp {
   EpiParams epi;
 };
 
+// WavLM positional convolution on the zero-padded, group-padded signal X [B * pslot (+ tail), 1024] (bf16) with the
+// block-diagonal weight W [1024, 128 taps * 64] (bf16). Output row r (flat over B * pslot) is routed by `epi`.
+struct PosConvOp {
+  const bf16* X;
+  long long x_rows;   // addressable rows of X (rows beyond read as zero)
+  const bf16* W;
+  int B, pslot;       // rows per clip in X
+  int rows_per_clip;  // output rows needed per clip (<= pslot - 128)
+  EpiParams epi;
+};
+
 // ---- launchers (each returns cudaError_t / sets message in err) ----
 int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err);
+int launch_posconv(const PosConvOp& op, cudaStream_t stream, int num_sms, std::string& err);
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows of pitch `pitch_elems`; box = 64 x box_rows; 128-byte swizzle.
 int make_tmap_2d(CUtensorMap* m, const void* base, unsigned long long dim0, unsigned long long dim1,

@@ -100,6 +100,7 @@ struct ssr_engine {
   int64_t launches = 0;
   // options
   int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1, opt_profile = 0, opt_attn_simt = 0;
+  int opt_posconv_generic = 0;  // 1: positional conv through the generic GEMM kernel (cross-check)
   std::vector<ProfEntry> prof;
   std::string prof_json;
 
@@ -884,22 +885,47 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
                               err))
         return -1;
     }
-    GemmOp op;
-    op.A = e->xp.as<bf16>();
-    op.lda = 1024;
-    op.a_rows = (long long)B * pslot + 128;
-    op.W = e->pos_w;
-    op.M = B * pslot;
-    op.N = 1024;
-    op.K = 8192;
-    op.a_mode = 1;
-    op.a_cols = 1024;
-    op.epi = epi_plain(nullptr, ACT_NONE, nullptr, 0, e->posconv.as<float>(), 1024, nullptr, 0);
-    if (run_gemm(e, op, st, "gemm_posconv")) return -1;
     const bool stable = d.stable_ln != 0;
     float* dst = stable ? e->h.as<float>() : e->tmp.as<float>();
-    e->launches++;
-    {
+    // With 64-channel groups (D = 1024) the conv epilogue finishes the stage in place:
+    //   h[b, t, :] = feat[b, t, :] + gelu(conv + bias)      for t < len_b
+    const bool fused_finish = (D == 1024) && !e->opt_simt && !e->opt_posconv_generic;
+    if (!e->opt_simt && !e->opt_posconv_generic) {
+      PosConvOp op;
+      op.X = e->xp.as<bf16>();
+      op.x_rows = (long long)B * pslot + 128;
+      op.W = e->pos_w;
+      op.B = B;
+      op.pslot = pslot;
+      op.rows_per_clip = slot;
+      if (fused_finish) {
+        op.epi = epi_plain(e->pos_b, ACT_GELU, e->feat.as<float>(), D, dst, D, nullptr, 0);
+        op.epi.in_slot = pslot;
+        op.epi.out_slot = slot;
+        op.epi.valid = slot;
+        op.epi.lens = e->lens_dev.as<int>();
+      } else {
+        op.epi = epi_plain(nullptr, ACT_NONE, nullptr, 0, e->posconv.as<float>(), 1024, nullptr, 0);
+      }
+      e->launches++;
+      ProfScope ps(e, st, "gemm_posconv", 2.0 * (double)B * slot * 1024.0 * 8192.0);
+      if (launch_posconv(op, st, e->num_sms, err)) return -1;
+    } else {
+      GemmOp op;
+      op.A = e->xp.as<bf16>();
+      op.lda = 1024;
+      op.a_rows = (long long)B * pslot + 128;
+      op.W = e->pos_w;
+      op.M = B * pslot;
+      op.N = 1024;
+      op.K = 8192;
+      op.a_mode = 1;
+      op.a_cols = 1024;
+      op.epi = epi_plain(nullptr, ACT_NONE, nullptr, 0, e->posconv.as<float>(), 1024, nullptr, 0);
+      if (run_gemm(e, op, st, "gemm_posconv")) return -1;
+    }
+    if (!fused_finish) {
+      e->launches++;
       ProfScope ps(e, st, "posconv_finish");
       if (launch_posconv_finish(e->posconv.as<float>(), pslot, e->pos_b, e->feat.as<float>(), B, slot, D,
                                 e->lens_dev.as<int>(), dst, st, err))
@@ -1138,6 +1164,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_profile = value;
   else if (k == "attn_simt")
     e->opt_attn_simt = value;
+  else if (k == "posconv_generic")
+    e->opt_posconv_generic = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;

@@ -508,6 +508,190 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ positional conv
+// WavLM's grouped positional convolution (16 groups x 64 channels, 128 taps, zero padding 64;
+// HF/models/wavlm/modeling_wavlm.py:48-90) as a Toeplitz GEMM:  out[t, g, co] = sum_tap sum_ci x[t + tap, g, ci] w.
+// A work item is (clip, 256-row tile, group). Its input window x[t0 .. t0+383, g*64 .. +64] is staged in shared
+// memory ONCE (48 KB, three TMA boxes); the A operand of tap `tap` is that same window shifted down by `tap` rows,
+// which costs nothing: the UMMA descriptor's start address simply moves by tap * 128 B. Measured on B200: the
+// 128B swizzle is applied to ABSOLUTE shared-memory address bits (both by TMA when writing and by the tensor core
+// when reading), so a start address that is only 128B- (not 1024B-) aligned needs no base-offset correction
+// (base_offset = tap & 7 or its complement give wrong results; 0 matches the generic-GEMM cross-check bit for bit).
+// Only the group's weights stream (8 KB per tap) through a TMA ring. Compared with re-loading a shifted A tile per
+// tap this removes ~2/3 of the L2 traffic.
+constexpr int PC_XWIN_BYTES = 3 * 128 * 128;  // 384 rows x 64 bf16
+constexpr int PC_W_BYTES = 64 * 64 * 2;
+constexpr int PC_WSTAGES = 8;
+constexpr int PC_BAR_OFF = 2 * PC_XWIN_BYTES + PC_WSTAGES * PC_W_BYTES;
+constexpr int PC_STAGE_OFF = PC_BAR_OFF + 256;
+constexpr int PC_SMEM_BYTES = PC_STAGE_OFF + 4 * (int)sizeof(EpiStage);
+
+struct PosConvParams {
+  int B, pslot, n_mt, n_items;  // rows per clip in X, 256-row tiles per clip, total items
+  GemmParams g;                 // M = B * pslot (flat X rows), N = 1024, epilogue
+};
+
+__global__ void __launch_bounds__(192, 1)
+posconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const PosConvParams pc) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
+  uint8_t* sX = smem;
+  uint8_t* sW = smem + 2 * PC_XWIN_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PC_BAR_OFF);
+  uint64_t* x_full = bars;                      // [2]
+  uint64_t* x_empty = bars + 2;                 // [2]
+  uint64_t* w_full = bars + 4;                  // [PC_WSTAGES]
+  uint64_t* w_empty = bars + 4 + PC_WSTAGES;    // [PC_WSTAGES]
+  uint64_t* tfull = bars + 4 + 2 * PC_WSTAGES;  // [2]
+  uint64_t* tempty = tfull + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  EpiStage* stages = reinterpret_cast<EpiStage*>(smem + PC_STAGE_OFF);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&x_full[i], 1);
+      mbar_init(&x_empty[i], 1);
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    for (int i = 0; i < PC_WSTAGES; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (clip b, row tile mt, group g); rowbase = first flat X row of the window = first flat output row
+  auto decode = [&](int idx, int& g, int& rowbase) {
+    g = idx & 15;
+    const int bm = idx >> 4;
+    const int b = bm / pc.n_mt, mt = bm - b * pc.n_mt;
+    rowbase = b * pc.pslot + mt * 256;
+  };
+
+  if (threadIdx.x == 128) {
+    // ===================== TMA producer =====================
+    uint32_t n = 0, nw = 0;
+    for (int idx = blockIdx.x; idx < pc.n_items; idx += gridDim.x, ++n) {
+      int g, rowbase;
+      decode(idx, g, rowbase);
+      const int xb = n & 1;
+      mbar_wait(&x_empty[xb], ((n >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx(&x_full[xb], PC_XWIN_BYTES);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        tma_load_2d(sX + xb * PC_XWIN_BYTES + i * 128 * 128, &tmX, &x_full[xb], g * 64, rowbase + i * 128);
+      for (int tap = 0; tap < 128; ++tap, ++nw) {
+        const int s = nw % PC_WSTAGES;
+        mbar_wait(&w_empty[s], ((nw / PC_WSTAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&w_full[s], PC_W_BYTES);
+        tma_load_2d(sW + s * PC_W_BYTES, &tmW, &w_full[s], tap * 64, g * 64);
+      }
+    }
+  } else if (threadIdx.x == 160) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    uint32_t n = 0, nw = 0;
+    for (int idx = blockIdx.x; idx < pc.n_items; idx += gridDim.x, ++n) {
+      const int xb = n & 1, acc = n & 1;
+      mbar_wait(&tempty[acc], ((n >> 1) & 1) ^ 1);
+      mbar_wait(&x_full[xb], (n >> 1) & 1);
+      tc_fence_after();
+      const uint64_t dx = umma_desc_sw128(smem_u32(sX + xb * PC_XWIN_BYTES));
+      for (int tap = 0; tap < 128; ++tap, ++nw) {
+        const int s = nw % PC_WSTAGES;
+        mbar_wait(&w_full[s], (nw / PC_WSTAGES) & 1);
+        tc_fence_after();
+        const uint64_t dw = umma_desc_sw128(smem_u32(sW + s * PC_W_BYTES));
+        // window shifted by `tap` rows: +tap*128 B in the descriptor's start-address field (16-byte units)
+        const uint64_t da = dx + (uint64_t)(tap * 8);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + acc * 128 + half * 64, da + (uint64_t)(half * 1024 + 2 * k), dw + 2 * k, idesc,
+                      (tap | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&w_empty[s]);
+      }
+      umma_commit(&x_empty[xb]);
+      umma_commit(&tfull[acc]);
+    }
+  } else if (warp < 4) {
+    // ===================== epilogue warps =====================
+    uint32_t n = 0;
+    for (int idx = blockIdx.x; idx < pc.n_items; idx += gridDim.x, ++n) {
+      int g, rowbase;
+      decode(idx, g, rowbase);
+      const int acc = n & 1;
+      const uint32_t par = (n >> 1) & 1;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half)
+        epilogue_tile<64, 1>(pc.g, stages[warp], tmem_base + acc * 128 + half * 64, warp,
+                             rowbase + half * 128 + (int)warp * 32, g * 64, lane, 0, &tfull[acc], par);
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_posconv(const PosConvOp& op, cudaStream_t stream, int num_sms, std::string& err) {
+  CUtensorMap tmX, tmW;
+  if (make_tmap_2d(&tmX, op.X, 1024ULL, (unsigned long long)op.x_rows, 1024ULL, 128, err)) return -1;
+  if (make_tmap_2d(&tmW, op.W, 8192ULL, 1024ULL, 8192ULL, 64, err)) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(posconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM_BYTES);
+    if (ce != cudaSuccess) {
+      err = std::string("cudaFuncSetAttribute(posconv_tc_kernel): ") + cudaGetErrorString(ce);
+      return -1;
+    }
+    attr_set = true;
+  }
+  PosConvParams pc;
+  pc.B = op.B;
+  pc.pslot = op.pslot;
+  pc.n_mt = ceil_div(op.rows_per_clip, 256);
+  pc.n_items = op.B * pc.n_mt * 16;
+  pc.g.M = op.B * op.pslot;
+  pc.g.N = 1024;
+  pc.g.K = 8192;
+  pc.g.a_mode = 1;
+  pc.g.num_m_tiles = pc.g.num_n_tiles = pc.g.num_kb = 0;
+  pc.g.epi = op.epi;
+  if ((op.epi.ldo32 & 3) || (op.epi.ldo16 & 7) || (op.epi.ldr & 3)) {
+    err = "posconv: output / residual leading dimensions must keep 16-byte row alignment";
+    return -1;
+  }
+  const int grid = pc.n_items < num_sms ? pc.n_items : num_sms;
+  posconv_tc_kernel<<<grid, 192, PC_SMEM_BYTES, stream>>>(tmX, tmW, pc);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    err = std::string("posconv_tc_kernel launch: ") + cudaGetErrorString(ce);
+    return -1;
+  }
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ SIMT debug kernel
 __device__ __forceinline__ void epi_scalar(const EpiParams& e, const RowInfo& ri, int c, float acc) {
   if (!ri.live) return;

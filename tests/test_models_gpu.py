@@ -115,6 +115,26 @@ def test_wavlm_vs_oracle_and_variants(name):
     simt = eng.pooled(clips)
     eng.set_option("simt_gemm", 0)
     check_pooled(simt, base, f"{name} tcgen05 vs SIMT GEMM", cos_min=0.99999, rel_max=8e-3)
+    eng.set_option("posconv_generic", 1)  # positional conv through the generic GEMM instead of the Toeplitz kernel
+    generic = eng.pooled(clips)
+    eng.set_option("posconv_generic", 0)
+    check_pooled(generic, base, f"{name} Toeplitz vs generic positional conv", cos_min=0.99999, rel_max=8e-3)
+    eng.set_option("attn_simt", 1)
+    mma = eng.pooled(clips)
+    eng.set_option("attn_simt", 0)
+    check_pooled(mma, base, f"{name} tcgen05 vs mma.sync attention", cos_min=0.99999, rel_max=8e-3)
+
+
+def test_wavlm_large_posconv_variants():
+    from ssr_b200 import synth
+
+    _, _, eng = wavlm("large")
+    clips = synth.mixed_clips()
+    base = eng.pooled(clips)
+    eng.set_option("posconv_generic", 1)
+    generic = eng.pooled(clips)
+    eng.set_option("posconv_generic", 0)
+    check_pooled(generic, base, "large: fused Toeplitz vs generic positional conv", cos_min=0.99999, rel_max=8e-3)
 
 
 def test_wavlm_stage_taps_vs_oracle():

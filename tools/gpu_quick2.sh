@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_kernels_gpu.py -q -p no:cacheprovider 2>&1 | tail -2
-timeout 900 python -m pytest tests/test_models_gpu.py -q -p no:cacheprovider -k "golden or variants" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_models_gpu.py -q -p no:cacheprovider -k "golden or variants or taps" 2>&1 | tail -2
 W=${WHISPER:-off}
 timeout 900 python bench.py --steps 5 --warmup 3 --whisper $W --no-cpu-baseline > gpurun_out/bench.log 2>&1
 python - <<'PY'
