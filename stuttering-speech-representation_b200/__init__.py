@@ -2,6 +2,7 @@
 
 The directory name mirrors the upstream repository; import it as `ssr_b200` (see /ssr_b200/__init__.py).
 """
+from . import pipeline  # noqa: F401
 from .engine import SsrError, WavLMEngine, WhisperEncoderEngine, iter_batches, shard_range  # noqa: F401
 from .extract import (  # noqa: F401
     extract_embeddings_from_audio_wavlm,

@@ -521,9 +521,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // tap this removes ~2/3 of the L2 traffic.
 constexpr int PC_XWIN_BYTES = 3 * 128 * 128;  // 384 rows x 64 bf16
 constexpr int PC_W_BYTES = 64 * 64 * 2;
-constexpr int PC_WSTAGES = 8;
+constexpr int PC_WSTAGES = 12;  // 96 KB of weight tiles in flight (TMA latency x 8 KB / ~300 cycles per tap)
 constexpr int PC_BAR_OFF = 2 * PC_XWIN_BYTES + PC_WSTAGES * PC_W_BYTES;
-constexpr int PC_STAGE_OFF = PC_BAR_OFF + 256;
+constexpr int PC_STAGE_OFF = PC_BAR_OFF + 512;  // (8 + 2 * PC_WSTAGES) mbarriers + the TMEM base slot
 constexpr int PC_SMEM_BYTES = PC_STAGE_OFF + 4 * (int)sizeof(EpiStage);
 
 struct PosConvParams {

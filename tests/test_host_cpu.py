@@ -158,3 +158,45 @@ def test_sharded_gather_world2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_pipeline_on_disk_contract_and_resume(tmp_path):
+    """files the reference's training scripts read (REF/model_training_1.py:112-161)."""
+    import pickle
+
+    from ssr_b200 import pipeline
+
+    clips = {f"/data/train_{i}.wav": np.full(100 + i, float(i), np.float32) for i in range(7)}
+    clips["/data/train_3.wav"] = None  # a clip that fails to load is skipped, as in REF/WavLM_embeddings.py:596-598
+    rows = [{"filename": os.path.basename(p), "path": p, "label": i % 2, "split": "train"}
+            for i, p in enumerate(clips)]
+    calls = []
+
+    def pooled_fn(batch):  # stand-in engine: [B, 3, 4], value = clip's first sample
+        calls.append(len(batch))
+        return np.stack([np.full((3, 4), c[0], np.float32) + np.arange(3, dtype=np.float32)[:, None] for c in batch])
+
+    out = str(tmp_path)
+    res = pipeline.extract_split(rows, pooled_fn, [2, 1, 9], out, "train", clips.get, batch_size=4,
+                                 checkpoint_interval=4)
+    assert calls == [3, 3] and len(res) == 6
+    meta, emb = pipeline.load_split(out, "train")
+    assert list(meta.columns) == ["filename", "path", "label", "split"] and len(meta) == 6
+    assert sorted(emb) == ["layer_1", "layer_2"]
+    assert emb["layer_2"].dtype == np.float32 and emb["layer_2"].shape == (6, 4)
+    order = [0, 1, 2, 4, 5, 6]
+    np.testing.assert_array_equal(emb["layer_1"][:, 0], np.array(order, np.float32) + 1)
+    assert list(meta["path"]) == [f"/data/train_{i}.wav" for i in order]
+    ck = sorted(os.listdir(os.path.join(out, "checkpoints")))
+    assert ck == ["checkpoint_train_0.pkl", "checkpoint_train_1.pkl"]
+    with open(os.path.join(out, "checkpoints", ck[-1]), "rb") as f:
+        saved = pickle.load(f)
+    assert len(saved) == 6 and set(saved[0]) == {"filename", "path", "label", "split", "layer_2", "layer_1"}
+    # resume: already processed paths are filtered out, nothing new is computed except the new file
+    clips["/data/train_7.wav"] = np.full(50, 7.0, np.float32)
+    rows.append({"filename": "train_7.wav", "path": "/data/train_7.wav", "label": 1, "split": "train"})
+    clips["/data/train_3.wav"] = None
+    calls.clear()
+    res2 = pipeline.extract_split(rows, pooled_fn, [2, 1], out, "train", clips.get, batch_size=4, resume=True)
+    assert calls == [1] and len(res2) == 7
+    assert pipeline.find_latest_checkpoint(out, "train") == 2

@@ -332,3 +332,22 @@ def test_batch_shims_match_per_clip_shims():
         assert list(one) == list(d) == ["layer_2", "layer_1", "layer_0"]
         for k in one:
             np.testing.assert_allclose(one[k], d[k], rtol=0, atol=2e-6 * max(1.0, np.abs(d[k]).max()))
+
+
+def test_pipeline_split_extraction_with_engine(tmp_path):
+    """SURVEY 8(f)-2 end to end: batched engine -> the reference's on-disk layout -> read back."""
+    from ssr_b200 import pipeline, synth
+
+    model, fe, eng = wavlm("tiny_post")
+    clips = {f"/d/train_{i}.wav": c for i, c in enumerate(synth.mixed_clips())}
+    rows = [{"filename": os.path.basename(p), "path": p, "label": i % 2, "split": "train"}
+            for i, p in enumerate(clips)]
+    n = model.config.num_hidden_layers + 1
+    idx = [n - 1, n - 2, n - 3, n // 2]
+    pipeline.extract_split(rows, eng.pooled, idx, str(tmp_path), "train", clips.get, batch_size=4)
+    meta, emb = pipeline.load_split(str(tmp_path), "train")
+    assert len(meta) == 5 and set(emb) == {f"layer_{i}" for i in set(idx)}
+    want = eng.pooled(list(clips.values()))
+    for i in set(idx):
+        assert emb[f"layer_{i}"].shape == (5, 768) and emb[f"layer_{i}"].dtype == np.float32
+        np.testing.assert_allclose(emb[f"layer_{i}"], want[:, i], rtol=0, atol=2e-6 * np.abs(want).max())
