@@ -87,6 +87,18 @@ int ssr_wavlm_pooled_host(ssr_engine* e, const float* audio_host, int64_t audio_
 int ssr_whisper_enc_pooled_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
                                 int32_t B, float* pooled_host);
 
+/* ---- Whisper encoder + decoder start-token probe -------------------------------------------
+ * Available when ssr_create received the decoder tensors: desc.reserved[0] = decoder_layers (Ld),
+ * desc.reserved[1] = decoder_ffn_dim, and weights "decoder.layers.{l}.*", "decoder.layer_norm.*" plus the two rows
+ * "decoder.embed_tokens.weight[0]" and "decoder.embed_positions.weight[0]" ([D] each: the reference feeds
+ * input_ids = [[0]], REF/whisper_embeddings_large.py:257-262).
+ * dec: float32 [B, Ld+1, D] with dec[b, i, :] == decoder hidden_states[i].squeeze(1) (REF :286-297); pooled as above. */
+int32_t ssr_decoder_layers(const ssr_engine* e);
+int ssr_whisper_full(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
+                     float* pooled_dev, float* dec_dev, void* cuda_stream);
+int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                          int32_t B, float* pooled_host, float* dec_host);
+
 /* Number of frames the model produces for a clip of n samples (WavLM conv arithmetic, HF modeling_wavlm.py:647-653;
  * Whisper: always 1500). */
 int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples);

@@ -124,3 +124,56 @@ class WhisperEncoderOracle:
     def pooled(self, audio, mel_filters) -> np.ndarray:
         mel = log_mel(audio, mel_filters)
         return np.stack([h.mean(axis=0) for h in self.hidden_states(mel)]).astype(np.float32)
+
+
+class WhisperDecoderTokenOracle:
+    """The reference's decoder probe (REF/whisper_embeddings_large.py:257-262, 286-297): ONE decoder step with
+    input_ids = [[0]] over the encoder's last_hidden_state; outputs are hidden_states[i].squeeze(1) (not pooled).
+    HF/models/whisper/modeling_whisper.py:449-506 (layer), :691-796 (decoder). With a single query token the causal
+    self-attention softmax is over one key, so its output is out_proj(v_proj(x)); q/k projections do not matter."""
+
+    def __init__(self, state_dict: dict, d_model: int, layers: int, heads: int, dtype=np.float32):
+        self.sd = {k: np.asarray(v) for k, v in state_dict.items()}
+        self.D, self.L, self.H = d_model, layers, heads
+        self.dt = dtype
+
+    @classmethod
+    def from_hf(cls, decoder, dtype=np.float32):
+        c = decoder.config
+        sd = {k: v.detach().cpu().numpy() for k, v in decoder.state_dict().items()}
+        return cls(sd, c.d_model, c.decoder_layers, c.decoder_attention_heads, dtype)
+
+    def w(self, name):
+        return self.sd[name].astype(self.dt)
+
+    def hidden_states(self, enc_last):
+        """enc_last: [1500, D] (encoder last_hidden_state of one clip) -> L+1 arrays [D]."""
+        enc = np.asarray(enc_last, self.dt)
+        D, H = self.D, self.H
+        h = self.w("embed_tokens.weight")[0] + self.w("embed_positions.weight")[0]
+        hs = [h]
+        for l in range(self.L):
+            p = f"layers.{l}"
+            x = layer_norm(h, self.w(p + ".self_attn_layer_norm.weight"), self.w(p + ".self_attn_layer_norm.bias"))
+            v = x @ self.w(p + ".self_attn.v_proj.weight").T + self.w(p + ".self_attn.v_proj.bias")
+            h = h + (v @ self.w(p + ".self_attn.out_proj.weight").T + self.w(p + ".self_attn.out_proj.bias"))
+            x = layer_norm(h, self.w(p + ".encoder_attn_layer_norm.weight"), self.w(p + ".encoder_attn_layer_norm.bias"))
+            q = (x @ self.w(p + ".encoder_attn.q_proj.weight").T + self.w(p + ".encoder_attn.q_proj.bias")) * self.dt(
+                (D // H) ** -0.5)
+            k = enc @ self.w(p + ".encoder_attn.k_proj.weight").T  # no bias
+            v = enc @ self.w(p + ".encoder_attn.v_proj.weight").T + self.w(p + ".encoder_attn.v_proj.bias")
+            qh = q.reshape(H, -1)                       # [H, 64]
+            kh = k.reshape(-1, H, D // H).transpose(1, 0, 2)  # [H, T, 64]
+            vh = v.reshape(-1, H, D // H).transpose(1, 0, 2)
+            s = np.einsum("hd,htd->ht", qh, kh)
+            s = s - s.max(axis=-1, keepdims=True)
+            pr = np.exp(s)
+            pr = pr / pr.sum(axis=-1, keepdims=True)
+            o = np.einsum("ht,htd->hd", pr, vh).reshape(D)
+            h = h + (o @ self.w(p + ".encoder_attn.out_proj.weight").T + self.w(p + ".encoder_attn.out_proj.bias"))
+            x = layer_norm(h, self.w(p + ".final_layer_norm.weight"), self.w(p + ".final_layer_norm.bias"))
+            y = gelu(x @ self.w(p + ".fc1.weight").T + self.w(p + ".fc1.bias")).astype(self.dt)
+            h = (h + (y @ self.w(p + ".fc2.weight").T + self.w(p + ".fc2.bias"))).astype(self.dt)
+            hs.append(h)
+        hs[-1] = layer_norm(h, self.w("layer_norm.weight"), self.w("layer_norm.bias"))
+        return hs

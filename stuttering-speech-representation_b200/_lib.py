@@ -40,6 +40,9 @@ SIGNATURES = {
     "ssr_logmel": (c_i32, [c_vp, c_vp, c_i64, c_i32p, c_i32, c_vp, c_vp]),
     "ssr_wavlm_pooled_host": (c_i32, [c_vp, c_vp, c_i64, c_i32p, c_i32, c_vp]),
     "ssr_whisper_enc_pooled_host": (c_i32, [c_vp, c_vp, c_i64, c_i32p, c_i32, c_vp]),
+    "ssr_decoder_layers": (c_i32, [c_vp]),
+    "ssr_whisper_full": (c_i32, [c_vp, c_vp, c_i64, c_i32p, c_i32, c_vp, c_vp, c_vp]),
+    "ssr_whisper_full_host": (c_i32, [c_vp, c_vp, c_i64, c_i32p, c_i32, c_vp, c_vp]),
     "ssr_num_frames": (c_i32, [c_vp, c_i32]),
     "ssr_launch_count": (c_i64, [c_vp]),
     "ssr_profile_fetch": (c_cp, [c_vp]),

@@ -90,6 +90,13 @@ struct LayerW {
   float gate_ba, gate_bb;
 };
 
+// Whisper decoder layer, single-token use: self-attention needs only v_proj / out_proj (softmax over one key).
+struct DecLayerW {
+  bf16 *w_sv, *w_so, *w_cq, *w_ck, *w_cv, *w_co, *w1, *w2;
+  float *b_sv, *b_so, *b_cq, *b_cv, *b_co, *b1, *b2;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+};
+
 }  // namespace
 
 struct ssr_engine {
@@ -124,6 +131,11 @@ struct ssr_engine {
   bf16 *wc1 = nullptr, *wc2 = nullptr;
   float *bc1 = nullptr, *bc2 = nullptr, *pos_emb = nullptr;
   std::vector<LayerW> layers;
+  // Whisper decoder (optional: present when the caller passed decoder.* tensors)
+  std::vector<DecLayerW> dec_layers;
+  int dec_L = 0, dec_F = 0;
+  float *dec_h0 = nullptr, *dec_ln_g = nullptr, *dec_ln_b = nullptr;
+  Buf dec_h, dec_x, dec_t1, dec_q, dec_qp, dec_scores, dec_ctx, dec_cv, dec_mid;
 
   // ---- workspace ----
   Buf nsamp_dev, lens_dev, stats, gn_acc;
@@ -431,6 +443,60 @@ int create_whisper(ssr_engine* e, WeightMap& w, std::string& err) {
     if (upload_f32(e, w.get(p + ".final_layer_norm.weight", D), D, &Lw.ln2_g, err)) return -1;
     if (upload_f32(e, w.get(p + ".final_layer_norm.bias", D), D, &Lw.ln2_b, err)) return -1;
   }
+  // ---- optional decoder (single-token probe): desc.reserved = {decoder_layers, decoder_ffn_dim} ----
+  const int Ld = d.reserved[0], Fd = d.reserved[1];
+  if (Ld > 0) {
+    if (Fd <= 0 || Fd % 256 != 0 || H > 20) {
+      err = "Whisper decoder: unsupported decoder_ffn_dim / head count";
+      return -1;
+    }
+    // token 0 at position 0: hidden_states[0] = embed_tokens.weight[0] + embed_positions.weight[0]
+    const float* et = w.get("decoder.embed_tokens.weight[0]", D);
+    const float* ep = w.get("decoder.embed_positions.weight[0]", D);
+    if (!et || !ep) return -1;
+    std::vector<float> h0(D);
+    for (int i = 0; i < D; ++i) h0[i] = et[i] + ep[i];
+    if (upload(e, h0, &e->dec_h0, err)) return -1;
+    if (upload_f32(e, w.get("decoder.layer_norm.weight", D), D, &e->dec_ln_g, err)) return -1;
+    if (upload_f32(e, w.get("decoder.layer_norm.bias", D), D, &e->dec_ln_b, err)) return -1;
+    e->dec_layers.resize(Ld);
+    const int64_t DD = (int64_t)D * D;
+    for (int l = 0; l < Ld; ++l) {
+      DecLayerW& W = e->dec_layers[l];
+      memset(&W, 0, sizeof(W));
+      const std::string p = "decoder.layers." + std::to_string(l);
+      if (upload_bf16(e, w.get(p + ".self_attn.v_proj.weight", DD), DD, 1.f, &W.w_sv, err)) return -1;
+      if (upload_f32(e, w.get(p + ".self_attn.v_proj.bias", D), D, &W.b_sv, err)) return -1;
+      if (upload_bf16(e, w.get(p + ".self_attn.out_proj.weight", DD), DD, 1.f, &W.w_so, err)) return -1;
+      if (upload_f32(e, w.get(p + ".self_attn.out_proj.bias", D), D, &W.b_so, err)) return -1;
+      if (upload_f32(e, w.get(p + ".self_attn_layer_norm.weight", D), D, &W.ln1_g, err)) return -1;
+      if (upload_f32(e, w.get(p + ".self_attn_layer_norm.bias", D), D, &W.ln1_b, err)) return -1;
+      // cross-attention: q pre-scaled by head_dim^-0.5 (exact: 1/8), k has no bias
+      if (upload_bf16(e, w.get(p + ".encoder_attn.q_proj.weight", DD), DD, 0.125f, &W.w_cq, err)) return -1;
+      {
+        const float* bq = w.get(p + ".encoder_attn.q_proj.bias", D);
+        if (!bq) return -1;
+        std::vector<float> b(bq, bq + D);
+        for (float& x : b) x *= 0.125f;
+        if (upload(e, b, &W.b_cq, err)) return -1;
+      }
+      if (upload_bf16(e, w.get(p + ".encoder_attn.k_proj.weight", DD), DD, 1.f, &W.w_ck, err)) return -1;
+      if (upload_bf16(e, w.get(p + ".encoder_attn.v_proj.weight", DD), DD, 1.f, &W.w_cv, err)) return -1;
+      if (upload_f32(e, w.get(p + ".encoder_attn.v_proj.bias", D), D, &W.b_cv, err)) return -1;
+      if (upload_bf16(e, w.get(p + ".encoder_attn.out_proj.weight", DD), DD, 1.f, &W.w_co, err)) return -1;
+      if (upload_f32(e, w.get(p + ".encoder_attn.out_proj.bias", D), D, &W.b_co, err)) return -1;
+      if (upload_f32(e, w.get(p + ".encoder_attn_layer_norm.weight", D), D, &W.ln2_g, err)) return -1;
+      if (upload_f32(e, w.get(p + ".encoder_attn_layer_norm.bias", D), D, &W.ln2_b, err)) return -1;
+      if (upload_bf16(e, w.get(p + ".fc1.weight", (int64_t)Fd * D), (int64_t)Fd * D, 1.f, &W.w1, err)) return -1;
+      if (upload_f32(e, w.get(p + ".fc1.bias", Fd), Fd, &W.b1, err)) return -1;
+      if (upload_bf16(e, w.get(p + ".fc2.weight", (int64_t)D * Fd), (int64_t)D * Fd, 1.f, &W.w2, err)) return -1;
+      if (upload_f32(e, w.get(p + ".fc2.bias", D), D, &W.b2, err)) return -1;
+      if (upload_f32(e, w.get(p + ".final_layer_norm.weight", D), D, &W.ln3_g, err)) return -1;
+      if (upload_f32(e, w.get(p + ".final_layer_norm.bias", D), D, &W.ln3_b, err)) return -1;
+    }
+    e->dec_L = Ld;
+    e->dec_F = Fd;
+  }
   return 0;
 }
 
@@ -716,6 +782,10 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
     a.eps = 1e-5f;
     a.out_f32 = tmp;
     a.ld_out32 = D;
+    if (!wavlm && e->dec_L > 0) {  // bf16 copy of last_hidden_state for the decoder's cross-attention
+      a.out_bf16 = xn;
+      a.ld_out16 = D;
+    }
     if (run_ln(e, a, st)) return -1;
     if (pool_into(e, tmp, B, slot, D, pooled, L, L1, st)) return -1;
     reg_dbg(e, "last_hidden", tmp, 0, M, D);
@@ -1000,12 +1070,114 @@ int whisper_logmel(ssr_engine* e, const float* audio, int64_t audio_ld, const in
   return launch_logmel(a, st, err);
 }
 
+// Decoder single-token probe over the encoder's last_hidden_state (bf16 copy in e->xn, written by run_layers):
+// dec_out[b, i, :] = decoder hidden_states[i] for the start token, i = 0..Ld.  See decoder.cu for the algebra.
+int whisper_decoder_token(ssr_engine* e, int B, float* dec_out, cudaStream_t st) {
+  std::string& err = e->err;
+  const int D = e->d.hidden, H = e->d.heads, Ld = e->dec_L, Fd = e->dec_F, T = 1500;
+  const long long ldo = (long long)(Ld + 1) * D;
+  if (e->dec_h.ensure((size_t)B * D * 4, st, err)) return -1;
+  if (e->dec_x.ensure((size_t)B * D * 2, st, err)) return -1;
+  if (e->dec_t1.ensure((size_t)B * D * 2, st, err)) return -1;
+  if (e->dec_q.ensure((size_t)B * D * 4, st, err)) return -1;
+  if (e->dec_qp.ensure((size_t)B * H * D * 4, st, err)) return -1;
+  if (e->dec_scores.ensure((size_t)B * H * T * 4, st, err)) return -1;
+  if (e->dec_ctx.ensure((size_t)4 * B * H * D * 4, st, err)) return -1;
+  if (e->dec_cv.ensure((size_t)B * D * 2, st, err)) return -1;
+  if (e->dec_mid.ensure((size_t)B * Fd * 2, st, err)) return -1;
+  float* h = e->dec_h.as<float>();
+  bf16* x = e->dec_x.as<bf16>();
+  bf16* t1 = e->dec_t1.as<bf16>();
+  bf16* cv = e->dec_cv.as<bf16>();
+  bf16* mid = e->dec_mid.as<bf16>();
+  float* q = e->dec_q.as<float>();
+
+  auto ln = [&](const float* g, const float* b, float* o32, long long ld32, bf16* o16) {
+    LayerNormArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in_f32 = h;
+    a.rows = B;
+    a.D = D;
+    a.ld_in = D;
+    a.gamma = g;
+    a.beta = b;
+    a.eps = 1e-5f;
+    a.out_f32 = o32;
+    a.ld_out32 = ld32;
+    a.out_bf16 = o16;
+    a.ld_out16 = D;
+    return run_ln(e, a, st);
+  };
+  auto save_state = [&](int i) -> int {
+    CK(cudaMemcpy2DAsync(dec_out + (long long)i * D, (size_t)ldo * 4, h, (size_t)D * 4, (size_t)D * 4, (size_t)B,
+                         cudaMemcpyDeviceToDevice, st));
+    return 0;
+  };
+
+  e->launches++;
+  if (launch_bcast_rows(e->dec_h0, h, B, D, D, st, err)) return -1;
+  if (save_state(0)) return -1;
+  for (int l = 0; l < Ld; ++l) {
+    const DecLayerW& W = e->dec_layers[l];
+    // self-attention over a single token == out_proj(v_proj(LN(h)))
+    if (ln(W.ln1_g, W.ln1_b, nullptr, 0, x)) return -1;
+    if (run_gemm(e, linear_op(x, B, D, W.w_sv, D, epi_plain(W.b_sv, ACT_NONE, nullptr, 0, nullptr, 0, t1, D)), st,
+                 "gemm_dec"))
+      return -1;
+    if (run_gemm(e, linear_op(t1, B, D, W.w_so, D, epi_plain(W.b_so, ACT_NONE, h, D, h, D, nullptr, 0)), st,
+                 "gemm_dec"))
+      return -1;
+    // cross-attention over the 1500 encoder states
+    if (ln(W.ln2_g, W.ln2_b, nullptr, 0, x)) return -1;
+    if (run_gemm(e, linear_op(x, B, D, W.w_cq, D, epi_plain(W.b_cq, ACT_NONE, nullptr, 0, q, D, nullptr, 0)), st,
+                 "gemm_dec"))
+      return -1;
+    {
+      DecCrossArgs a;
+      a.q = q;
+      a.wk = W.w_ck;
+      a.wv = W.w_cv;
+      a.bv = W.b_cv;
+      a.enc = e->xn.as<bf16>();
+      a.qp = e->dec_qp.as<float>();
+      a.scores = e->dec_scores.as<float>();
+      a.ctx_part = e->dec_ctx.as<float>();
+      a.out = cv;
+      a.B = B;
+      a.T = T;
+      a.D = D;
+      a.H = H;
+      e->launches += 5;
+      ProfScope ps(e, st, "dec_cross_attention", 4.0 * (double)B * H * T * D);
+      if (launch_dec_cross_attention(a, st, err)) return -1;
+    }
+    if (run_gemm(e, linear_op(cv, B, D, W.w_co, D, epi_plain(W.b_co, ACT_NONE, h, D, h, D, nullptr, 0)), st,
+                 "gemm_dec"))
+      return -1;
+    // feed-forward
+    if (ln(W.ln3_g, W.ln3_b, nullptr, 0, x)) return -1;
+    if (run_gemm(e, linear_op(x, B, D, W.w1, Fd, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, Fd)), st,
+                 "gemm_dec"))
+      return -1;
+    if (run_gemm(e, linear_op(mid, B, Fd, W.w2, D, epi_plain(W.b2, ACT_NONE, h, D, h, D, nullptr, 0)), st,
+                 "gemm_dec"))
+      return -1;
+    if (l < Ld - 1 && save_state(l + 1)) return -1;
+  }
+  // hidden_states[Ld] = decoder.layer_norm(h), written straight into its output slot
+  return ln(e->dec_ln_g, e->dec_ln_b, dec_out + (long long)Ld * D, ldo, nullptr);
+}
+
 int whisper_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int32_t* n_samples, int B,
-                    float* pooled, cudaStream_t st) {
+                    float* pooled, cudaStream_t st, float* dec_out = nullptr) {
   std::string& err = e->err;
   const ssr_model_desc& d = e->d;
   const int D = d.hidden, L1 = d.layers + 1;
   if (B <= 0) return 0;
+  if (dec_out != nullptr && e->dec_L == 0) {
+    err = "this Whisper engine was created without decoder weights";
+    return -1;
+  }
   if ((long long)B * 3002 > 2000000000LL / 1) {
     err = "batch too large";
     return -1;
@@ -1073,7 +1245,9 @@ int whisper_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const i
     }
     if (e->opt_snapshot_layer >= 0 && snapshot(e, 7, "hs0", e->h.p, 0, M, D, st)) return -1;
   }
-  return run_layers(e, B, 1500, true, false, pooled, st);
+  if (run_layers(e, B, 1500, true, false, pooled, st)) return -1;
+  if (dec_out != nullptr) return whisper_decoder_token(e, B, dec_out, st);
+  return 0;
 }
 
 cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -1261,6 +1435,53 @@ int ssr_whisper_enc_pooled_host(ssr_engine* e, const float* audio_host, int64_t 
     return -1;
   }
   return run_host(e, false, audio_host, audio_ld, n_samples, B, pooled_host);
+}
+
+int32_t ssr_decoder_layers(const ssr_engine* e) { return e ? e->dec_L : -1; }
+
+int ssr_whisper_full(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
+                     float* pooled_dev, float* dec_dev, void* cuda_stream) {
+  if (!e) return -1;
+  if (e->d.family != SSR_WHISPER_ENC) {
+    e->err = "engine is not a Whisper engine";
+    return -1;
+  }
+  if (!audio_dev || !n_samples || !pooled_dev || !dec_dev || B < 0) {
+    e->err = "ssr_whisper_full: null argument";
+    return -1;
+  }
+  cudaSetDevice(e->device);
+  return whisper_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, as_stream(cuda_stream), dec_dev);
+}
+
+int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
+                          int32_t B, float* pooled_host, float* dec_host) {
+  if (!e) return -1;
+  std::string& err = e->err;
+  if (e->d.family != SSR_WHISPER_ENC) {
+    err = "engine is not a Whisper engine";
+    return -1;
+  }
+  if (!audio_host || !n_samples || !pooled_host || !dec_host || B < 0) {
+    err = "ssr_whisper_full_host: null argument";
+    return -1;
+  }
+  if (B == 0) return 0;
+  cudaSetDevice(e->device);
+  cudaStream_t st = nullptr;
+  const size_t in_bytes = (size_t)B * audio_ld * 4;
+  const size_t enc_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
+  const size_t dec_bytes = (size_t)B * (e->dec_L + 1) * e->d.hidden * 4;
+  if (e->audio_stage.ensure(in_bytes, st, err)) return -1;
+  if (e->pooled_stage.ensure(enc_bytes + dec_bytes, st, err)) return -1;
+  float* enc_dev = e->pooled_stage.as<float>();
+  float* dec_dev = reinterpret_cast<float*>(reinterpret_cast<char*>(e->pooled_stage.p) + enc_bytes);
+  CK(cudaMemcpyAsync(e->audio_stage.p, audio_host, in_bytes, cudaMemcpyHostToDevice, st));
+  if (whisper_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B, enc_dev, st, dec_dev)) return -1;
+  CK(cudaMemcpyAsync(pooled_host, enc_dev, enc_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(dec_host, dec_dev, dec_bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples) {

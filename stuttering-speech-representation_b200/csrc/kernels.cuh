@@ -52,6 +52,22 @@ struct AttentionArgs {
 int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);      // mma.sync (debug / tiny T)
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
 
+// Whisper decoder single-token cross-attention (decoder.cu). All token-level tensors have one row per clip.
+struct DecCrossArgs {
+  const float* q;     // [B, D] fp32 : (Wq x + bq) * head_dim^-0.5
+  const bf16* wk;     // [D, D] encoder_attn.k_proj.weight (no bias)
+  const bf16* wv;     // [D, D] encoder_attn.v_proj.weight
+  const float* bv;    // [D]
+  const bf16* enc;    // [B * T, D] encoder last_hidden_state (bf16 copy)
+  float* qp;          // scratch [B, H, D]
+  float* scores;      // scratch [B, H, T]
+  float* ctx_part;    // scratch [4, B, H, D]
+  bf16* out;          // [B, D] attention output before out_proj (bf16: next GEMM's A operand)
+  int B, T, D, H;
+};
+int launch_dec_cross_attention(const DecCrossArgs& a, cudaStream_t st, std::string& err);
+int launch_bcast_rows(const float* v, float* out, int B, int D, long long ld, cudaStream_t st, std::string& err);
+
 // WavLM waveform statistics + first conv layer (C_in = 1, k = 10, stride 5) fused with its normalisation + GELU.
 struct Conv0Args {
   const float* audio;  // [B, audio_ld]

@@ -233,16 +233,36 @@ class WhisperEncoderEngine(_EngineBase):
         if config.activation_function != "gelu":
             raise SsrError("unsupported Whisper config: activation must be erf-GELU")
         tensors = {}
+        has_decoder = False
         for k, v in state_dict.items():
-            for pref in ("model.encoder.", "encoder."):
-                if k.startswith(pref):
-                    k = k[len(pref):]
-                    break
-            else:
-                if k.startswith(("decoder.", "model.decoder.", "proj_out.")):
+            if k.startswith("model."):
+                k = k[len("model."):]
+            if k.startswith("decoder."):
+                # decoder start-token probe (REF/whisper_embeddings_large.py:257-262): only row 0 of the two
+                # embedding tables is needed; the single-token self-attention never touches q_proj / k_proj.
+                if k in ("decoder.embed_tokens.weight", "decoder.embed_positions.weight"):
+                    tensors[k + "[0]"] = v[0].detach().to(torch.float32).cpu().numpy()
+                    has_decoder = True
+                elif ".self_attn.q_proj." in k or ".self_attn.k_proj." in k:
                     continue
+                else:
+                    tensors[k] = v.detach().to(torch.float32).cpu().numpy()
+                continue
+            if k.startswith("encoder."):
+                k = k[len("encoder."):]
+            elif k.startswith("proj_out."):
+                continue
             if k.startswith(("conv1.", "conv2.", "embed_positions.", "layers.", "layer_norm.")):
                 tensors[k] = v.detach().to(torch.float32).cpu().numpy()
+        self.decoder_layers = 0
+        if has_decoder:
+            if config.decoder_attention_heads != config.encoder_attention_heads:
+                raise SsrError("unsupported Whisper config: decoder and encoder head counts differ")
+            if getattr(config, "scale_embedding", False):
+                raise SsrError("unsupported Whisper config: scale_embedding")
+            desc.reserved[0] = config.decoder_layers
+            desc.reserved[1] = config.decoder_ffn_dim
+            self.decoder_layers = int(config.decoder_layers)
         if mel_filters is None:
             mel_filters = whisper_mel_filters(config.num_mel_bins)
         mel_filters = np.asarray(mel_filters, dtype=np.float32)
@@ -272,7 +292,30 @@ class WhisperEncoderEngine(_EngineBase):
                 raise SsrError("unsupported WhisperFeatureExtractor: dither must be 0")
             if bool(getattr(fe, "do_normalize", False)):
                 raise SsrError("unsupported WhisperFeatureExtractor: do_normalize must be False")
-        return cls({"encoder." + k: v for k, v in enc.state_dict().items()}, enc.config, mel, device)
+        sd = {"encoder." + k: v for k, v in enc.state_dict().items()}
+        full = getattr(model, "model", model)  # WhisperForConditionalGeneration -> WhisperModel
+        dec = getattr(full, "decoder", None)
+        if dec is not None and hasattr(dec, "state_dict"):
+            sd.update({"decoder." + k: v for k, v in dec.state_dict().items()})
+        return cls(sd, enc.config, mel, device)
+
+    def pooled_with_decoder(self, clips: Sequence) -> tuple[np.ndarray, np.ndarray]:
+        """(encoder pooled [B, Le+1, D], decoder start-token hidden states [B, Ld+1, D]) — everything
+        REF/whisper_embeddings_large.py:234-299 derives its `encoder_layer_*` / `decoder_layer_*` outputs from."""
+        if self.decoder_layers == 0:
+            raise SsrError("this engine was built without decoder weights")
+        B = len(clips)
+        if B == 0:
+            return (np.zeros((0, self.layers + 1, self.hidden), np.float32),
+                    np.zeros((0, self.decoder_layers + 1, self.hidden), np.float32))
+        buf, n = self._stage(clips)
+        enc = torch.empty((B, self.layers + 1, self.hidden), dtype=torch.float32).pin_memory()
+        dec = torch.empty((B, self.decoder_layers + 1, self.hidden), dtype=torch.float32).pin_memory()
+        rc = self._lib.ssr_whisper_full_host(self._h, buf.data_ptr(), buf.stride(0), n.ctypes.data_as(_lib.c_i32p), B,
+                                             enc.data_ptr(), dec.data_ptr())
+        if rc != 0:
+            raise SsrError(self._err())
+        return enc.numpy().copy(), dec.numpy().copy()
 
     def logmel_device(self, audio: torch.Tensor, n_samples, stream=None) -> torch.Tensor:
         """== WhisperFeatureExtractor(audio).input_features : CUDA float32 [B, 80, 3000]."""

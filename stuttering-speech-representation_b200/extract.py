@@ -12,7 +12,9 @@ nothing is raised to the caller (REF/WavLM_embeddings.py:329-341).  The `model` 
 the HF objects the reference scripts already hold; an engine is built from them once and cached per model object.
 The `device` argument is accepted for signature compatibility: the engine always runs on CUDA.
 
-`decoder_layer_*` entries are OUT OF SCOPE of this path: they are skipped with a warning.
+`decoder_layer_*` entries (the reference's single start-token decoder pass) are produced when the
+model object handed in has a decoder (WhisperModel / WhisperForConditionalGeneration); with a bare WhisperEncoder they
+are skipped with a warning.
 
 Batched entry points (`*_batch`) are the efficient way in: the reference's per-clip loop costs one H2D / D2H
 round trip per clip.
@@ -135,25 +137,31 @@ def extract_wavlm_embeddings_batch(audio_arrays, model, feature_extractor, devic
 
 
 # ---------------------------------------------------------------------------------------------- Whisper
-def _whisper_dict(pooled_clip, encoder_indices, decoder_names):
-    out = pooled_to_layer_dict(pooled_clip, encoder_indices, "encoder_layer_")
-    for nm in decoder_names:
-        logger.warning(f"{nm}: the Whisper decoder pass is outside this engine's scope; entry skipped")
-    return out
+def _whisper_states(eng, audio_array, want_decoder: bool):
+    """(encoder pooled [Le+1, D], decoder start-token states [Ld+1, D] or None) for one clip. The decoder probe runs
+    when the engine was built from a model that has a decoder (WhisperModel); a bare encoder yields None."""
+    if want_decoder and getattr(eng, "decoder_layers", 0) > 0:
+        enc, dec = eng.pooled_with_decoder([audio_array])
+        return enc[0], dec[0]
+    return eng.pooled([audio_array])[0], None
 
 
 def extract_embeddings_from_audio_whisper(audio_array, model, processor, device, layer_names):
     try:
         eng = get_engine(model, processor, device)
-        pooled = eng.pooled([audio_array])[0]
+        enc, dec = _whisper_states(eng, audio_array, any(n.startswith("decoder_layer_") for n in layer_names))
         out = {}
-        for layer_name in layer_names:
+        for layer_name in layer_names:  # REF/model_training_1.py:300-312
             if layer_name.startswith("encoder_layer_"):
                 idx = int(layer_name.split("_")[-1])
-                if idx < pooled.shape[0]:
-                    out[layer_name] = np.ascontiguousarray(pooled[idx], dtype=np.float32).flatten()
+                if idx < enc.shape[0]:
+                    out[layer_name] = np.ascontiguousarray(enc[idx], dtype=np.float32).flatten()
             elif layer_name.startswith("decoder_layer_"):
-                logger.warning(f"{layer_name}: the Whisper decoder pass is outside this engine's scope; skipped")
+                idx = int(layer_name.split("_")[-1])
+                if dec is None:
+                    logger.warning(f"{layer_name}: engine was built from an encoder-only model; skipped")
+                elif idx < dec.shape[0]:
+                    out[layer_name] = np.ascontiguousarray(dec[idx], dtype=np.float32).flatten()
         return out
     except Exception as e:  # noqa: BLE001
         logger.error(f"Error extracting Whisper embeddings: {e}")
@@ -166,8 +174,18 @@ def extract_whisper_embeddings_fixed(audio_file, model, processor, device, encod
         return None
     try:
         eng = get_engine(model, processor, device)
-        pooled = eng.pooled([audio_array])[0]
-        return _whisper_dict(pooled, encoder_indices, [f"decoder_layer_{i}" for i in decoder_indices])
+        enc, dec = _whisper_states(eng, audio_array, len(decoder_indices) > 0)
+        out = pooled_to_layer_dict(enc, encoder_indices, "encoder_layer_")  # REF/whisper_embeddings_large.py:272-283
+        if dec is not None:
+            for idx in decoder_indices:  # REF/whisper_embeddings_large.py:286-297
+                if idx < dec.shape[0]:
+                    out[f"decoder_layer_{idx}"] = np.ascontiguousarray(dec[idx], dtype=np.float32).flatten()
+                else:
+                    logger.warning(f"Decoder layer {idx} is out of range (max: {dec.shape[0] - 1})")
+        else:
+            for idx in decoder_indices:
+                logger.warning(f"decoder_layer_{idx}: engine was built from an encoder-only model; skipped")
+        return out
     except Exception as e:  # noqa: BLE001
         logger.error(f"Error extracting Whisper embeddings: {e}")
         return None

@@ -94,6 +94,31 @@ def build_whisper_encoder(name: str, seed: int = 0):
     return enc, WhisperFeatureExtractor()
 
 
+def whisper_full_config(name: str):
+    """Configs WITH a decoder (for the decoder_layer_* outputs of REF/whisper_embeddings_large.py:286-297)."""
+    from transformers import WhisperConfig
+
+    if name == "tiny_full":
+        return WhisperConfig(d_model=256, encoder_layers=2, encoder_attention_heads=4, encoder_ffn_dim=1024,
+                             decoder_layers=2, decoder_attention_heads=4, decoder_ffn_dim=512, num_mel_bins=80,
+                             vocab_size=51865)
+    if name == "mid_full":
+        return WhisperConfig(d_model=768, encoder_layers=3, encoder_attention_heads=12, encoder_ffn_dim=3072,
+                             decoder_layers=4, decoder_attention_heads=12, decoder_ffn_dim=3072, num_mel_bins=80,
+                             vocab_size=51865)
+    raise KeyError(name)
+
+
+def build_whisper_model(name: str, seed: int = 0):
+    """(WhisperModel, feature_extractor) with encoder AND decoder, random init, as the reference holds it
+    (REF/whisper_embeddings_large.py:431-438)."""
+    import torch
+    from transformers import WhisperFeatureExtractor, WhisperModel
+
+    torch.manual_seed(seed)
+    return WhisperModel(whisper_full_config(name)).eval(), WhisperFeatureExtractor()
+
+
 def state_checksum(model) -> float:
     """Cheap fingerprint of seeded weights (guards golden fixtures against RNG drift)."""
     import torch

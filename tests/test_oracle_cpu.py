@@ -156,6 +156,28 @@ def test_whisper_oracle_vs_reference_golden():
     assert np.abs(mel[:, :, ::7] - gm["mel_sub"]).max() < 2e-5
 
 
+def test_whisper_decoder_oracle_vs_reference_golden():
+    """decoder_layer_* of the reference (full WhisperModel through REF extract_whisper_embeddings_fixed)."""
+    from oracle.whisper_oracle import WhisperDecoderTokenOracle, WhisperEncoderOracle, log_mel
+    from ssr_b200 import synth
+    from ssr_b200.melfilters import whisper_mel_filters
+
+    g = golden("whisper_tiny_full")
+    model, fe = synth.build_whisper_model("tiny_full")
+    assert abs(synth.state_checksum(model) - float(g["checksum"])) <= 1e-9 * float(g["checksum"])
+    eo = WhisperEncoderOracle.from_hf(model.encoder)
+    do = WhisperDecoderTokenOracle.from_hf(model.decoder)
+    clips = synth.mixed_clips()[:4]
+    mf = whisper_mel_filters(80)
+    for i in (0, 3):
+        hs = eo.hidden_states(log_mel(clips[i], mf))
+        enc = np.stack([h.mean(0) for h in hs])
+        dec = np.stack(do.hidden_states(hs[-1]))
+        assert rel_err(enc[None], g["encoder"][i][None]) < 5e-5
+        assert rel_err(dec[None], g["decoder"][i][None]) < 5e-5
+    assert g["decoder"].shape == (4, 3, 256)
+
+
 def test_golden_fixture_shapes():
     assert golden("wavlm_base_plus")["pooled"].shape == (8, 13, 768)
     assert golden("wavlm_large")["pooled"].shape == (7, 25, 1024)

@@ -118,6 +118,27 @@ def main():
         clips = [synth.noise_clips(1, 48000, seed=1234)[0], synth.tonal_clip(48000)]
         pooled, ck = run_whisper(ref_whisper, "large", clips)
         np.savez_compressed(os.path.join(OUT, "whisper_large.npz"), pooled=pooled, checksum=ck)
+    # full Whisper models (encoder + decoder): every encoder_layer_* AND decoder_layer_* output of the reference
+    for full in ("tiny_full", "mid_full"):
+        if want("whisper_" + full):
+            model, fe = synth.build_whisper_model(full, 0)
+            ne, nd = model.config.encoder_layers + 1, model.config.decoder_layers + 1
+            clips = synth.mixed_clips()[:4]
+            table = {f"clip{i}": c for i, c in enumerate(clips)}
+            ref_whisper.load_audio = lambda path, target_sr=16000: table[path]
+            enc = np.zeros((len(clips), ne, model.config.d_model), np.float32)
+            dec = np.zeros((len(clips), nd, model.config.d_model), np.float32)
+            for i in range(len(clips)):
+                emb = ref_whisper.extract_whisper_embeddings_fixed(f"clip{i}", model, fe, torch.device("cpu"),
+                                                                   list(range(ne)), list(range(nd)))
+                assert emb is not None and len(emb) == ne + nd
+                for j in range(ne):
+                    enc[i, j] = emb[f"encoder_layer_{j}"]
+                for j in range(nd):
+                    dec[i, j] = emb[f"decoder_layer_{j}"]
+            np.savez_compressed(os.path.join(OUT, f"whisper_{full}.npz"), encoder=enc, decoder=dec,
+                                checksum=synth.state_checksum(model))
+            print(f"  whisper {full}: {len(clips)} clips (encoder + decoder)")
     # log-mel front end alone: HF WhisperFeatureExtractor (the call at REF/whisper_embeddings_large.py:242-246),
     # every 7th frame kept to bound the fixture size
     if want("logmel"):
