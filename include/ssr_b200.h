@@ -136,6 +136,37 @@ int ssr_attention(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t slot,
 int ssr_pool_mean(const float* x, int32_t B, int32_t slot, int32_t D, const int32_t* lens_dev, float* pooled,
                   int64_t pooled_ld, void* cuda_stream, char* err, int32_t err_len);
 
+/* ---- waveform augmentation, batched on the device. Engine-independent.
+ * Replaces augment_audio of /root/reference/model_training_1.py:166-213 and model_training_01.py:140-192 (kinds
+ * speed / noise / volume / none; the decision which kind and which factor stays on the host, drawn exactly like the
+ * reference draws it, see stuttering-speech-representation_b200/augment.py). The speed kind is torchaudio's
+ * Resample(sr -> new_rate) followed by Resample(new_rate -> sr) (sinc_interp_hann, width 6, rolloff 0.99); every
+ * kind ends with clamp(-1, 1) (model_training_1.py:204). */
+enum { SSR_AUG_NONE = 0, SSR_AUG_SPEED = 1, SSR_AUG_NOISE = 2, SSR_AUG_VOLUME = 3 };
+
+typedef struct ssr_aug_op {
+  int32_t kind;     /* SSR_AUG_* */
+  int32_t new_rate; /* speed: int(sample_rate * speed_factor), model_training_1.py:185 */
+  float factor;     /* noise: noise_factor; volume: volume_factor */
+  int32_t reserved;
+  uint64_t seed;    /* noise without caller-supplied normals: key of the counter-based generator */
+} ssr_aug_op;
+
+/* torchaudio's output length of one Resample(orig_rate -> new_rate) over n samples. */
+int32_t ssr_resample_length(int32_t n, int32_t orig_rate, int32_t new_rate);
+/* Output length of one augmentation op over n samples (speed: the round trip; else n). */
+int32_t ssr_augment_out_length(const ssr_aug_op* op, int32_t n, int32_t sample_rate);
+/* Bytes of device scratch ssr_augment needs for this batch. */
+int64_t ssr_augment_work_bytes(const int32_t* n_in, int32_t batch, const ssr_aug_op* ops, int32_t sample_rate);
+/* audio_dev: float32 [batch, in_stride] on the device, clip b has n_in[b] (host array) samples. ops: host array.
+ * noise_dev (optional): float32 [batch, noise_stride] standard normals, used as-is by the noise kind (replaying the
+ * reference's torch.randn_like stream gives bit-identical output); NULL = generate on the device (Philox4x32-10
+ * keyed by (op.seed, sample): give every clip its own seed). out_dev: float32 [batch, out_stride]; samples beyond n_out[b] are zero-filled.
+ * n_out: host array, filled before return. Asynchronous on the stream. */
+int ssr_augment(const float* audio_dev, int64_t in_stride, const int32_t* n_in, int32_t batch, const ssr_aug_op* ops,
+                int32_t sample_rate, const float* noise_dev, int64_t noise_stride, void* work_dev, int64_t work_bytes,
+                float* out_dev, int64_t out_stride, int32_t* n_out, void* cuda_stream, char* err, int32_t err_len);
+
 /* ---- debug taps: copy a named internal buffer of the last run to host (synchronises). Returns bytes copied,
  * or a negative error. With dst == NULL returns the buffer's size in bytes. `dims` (optional, 4 entries) gets the
  * logical shape, `dtype` (optional) 0 = float32, 1 = bfloat16. */

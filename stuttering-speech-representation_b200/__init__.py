@@ -2,7 +2,8 @@
 
 The directory name mirrors the upstream repository; import it as `ssr_b200` (see /ssr_b200/__init__.py).
 """
-from . import pipeline  # noqa: F401
+from . import augment, pipeline  # noqa: F401
+from .augment import augment_and_extract, augment_audio  # noqa: F401
 from .engine import SsrError, WavLMEngine, WhisperEncoderEngine, iter_batches, shard_range  # noqa: F401
 from .extract import (  # noqa: F401
     extract_embeddings_from_audio_wavlm,
@@ -16,5 +17,6 @@ from .extract import (  # noqa: F401
 __all__ = [
     "SsrError", "WavLMEngine", "WhisperEncoderEngine", "iter_batches", "shard_range",
     "extract_wavlm_embeddings", "extract_embeddings_from_audio_wavlm", "extract_whisper_embeddings_fixed",
-    "extract_embeddings_from_audio_whisper", "get_engine", "pooled_to_layer_dict",
+    "extract_embeddings_from_audio_whisper", "get_engine", "pooled_to_layer_dict", "augment_audio",
+    "augment_and_extract",
 ]

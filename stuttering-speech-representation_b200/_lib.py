@@ -29,6 +29,14 @@ class Weight(C.Structure):
     _fields_ = [("name", c_cp), ("data", c_vp), ("numel", c_i64)]
 
 
+SSR_AUG_NONE, SSR_AUG_SPEED, SSR_AUG_NOISE, SSR_AUG_VOLUME = 0, 1, 2, 3
+
+
+class AugOp(C.Structure):
+    _fields_ = [("kind", c_i32), ("new_rate", c_i32), ("factor", C.c_float), ("reserved", c_i32),
+                ("seed", C.c_uint64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ssr_b200.h declares (tests check this).
 SIGNATURES = {
     "ssr_create": (c_i32, [C.POINTER(ModelDesc), C.POINTER(Weight), c_i32, c_i32, C.POINTER(c_vp)]),
@@ -55,6 +63,11 @@ SIGNATURES = {
                               c_i32]),
     "ssr_pool_mean": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_cp, c_i32]),
     "ssr_debug_fetch": (c_i64, [c_vp, c_cp, c_vp, c_i64, c_i64p, c_i32p]),
+    "ssr_resample_length": (c_i32, [c_i32, c_i32, c_i32]),
+    "ssr_augment_out_length": (c_i32, [C.POINTER(AugOp), c_i32, c_i32]),
+    "ssr_augment_work_bytes": (c_i64, [c_i32p, c_i32, C.POINTER(AugOp), c_i32]),
+    "ssr_augment": (c_i32, [c_vp, c_i64, c_i32p, c_i32, C.POINTER(AugOp), c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
+                            c_i32p, c_vp, c_cp, c_i32]),
 }
 
 _lib = None

@@ -37,6 +37,15 @@ def mixed_clips() -> list[np.ndarray]:
     return [a[0], a[1][:40000], tonal_clip(48000), a[2][:16000], np.zeros(32000, np.float32)]
 
 
+def aug_clips() -> list[np.ndarray]:
+    """Clips for the augmentation parity cases: noise, a loud chirp that exceeds +-1 once amplified (so the final
+    clamp bites), and a short clip of odd length."""
+    a = noise_clips(2, 48000, seed=21)
+    t = np.arange(40000, dtype=np.float64) / 16000.0
+    chirp = (0.97 * np.sin(2 * np.pi * (200.0 * t + 300.0 * t * t))).astype(np.float32)
+    return [a[0], chirp, a[1][:16001]]
+
+
 # ------------------------------------------------------------------------------------------------ model configs
 def wavlm_config(name: str):
     from transformers import WavLMConfig

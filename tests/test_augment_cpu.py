@@ -1,0 +1,121 @@
+"""CPU tier for the augmentation row: the numpy oracle against the fixture produced by the
+reference's own augment_audio (tools/make_golden_aug.py), plus the host-side decision logic of the product."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "augment.npz")
+SUB = 4
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def case_args(name):
+    variant, kind, seed = name.split("/")
+    seed = int(seed)
+    return variant, kind, seed, seed % 3 if kind != "none" else 1
+
+
+def test_fixture_covers_every_kind(gold):
+    names = [str(n) for n in gold["names"]]
+    assert len(names) >= 20
+    for k in ("speed", "noise", "volume", "random", "none"):
+        assert any(f"/{k}/" in n for n in names)
+
+
+def test_oracle_vs_reference_golden(gold):
+    import torch
+
+    from oracle import augment_oracle as ao
+    from ssr_b200 import synth
+
+    clips = synth.aug_clips()
+    worst = 0.0
+    for name in (str(n) for n in gold["names"]):
+        variant, kind, seed, ci = case_args(name)
+        random.seed(seed)
+        torch.manual_seed(seed)
+        out = ao.augment_audio(clips[ci].copy(), augmentation_type=kind, variant=variant)
+        assert out.dtype == np.float32 and out.shape[0] == int(gold[name + "/len"]), name
+        ref = gold[name + "/sub"]
+        err = float(np.abs(out[::SUB] - ref).max())
+        worst = max(worst, err)
+        random.seed(seed)
+        drawn = ao.draw(kind, 16000, variant)[0]
+        if drawn == "speed":
+            assert err <= 1e-6, (name, err)  # fp32 conv summation order
+        else:
+            assert err == 0.0, (name, err)   # elementwise kinds are bit-exact
+        assert abs(float(out.astype(np.float64).sum()) - float(gold[name + "/sum"])) <= 2e-3
+        assert abs(float((out.astype(np.float64) ** 2).sum()) - float(gold[name + "/sumsq"])) <= 2e-3
+    assert worst > 0.0  # the speed cases are not trivially identical
+
+
+@pytest.mark.parametrize("nr", [16001, 15200, 16777])
+def test_oracle_resampler_vs_torchaudio_golden(gold, nr):
+    from oracle import augment_oracle as ao
+    from ssr_b200 import synth
+
+    x = synth.aug_clips()[0][:24000]
+    mid = ao.sinc_resample(x, 16000, nr)
+    out = ao.sinc_resample(mid, nr, 16000)
+    assert [mid.shape[0], out.shape[0]] == list(gold[f"resample/{nr}/lens"])
+    assert np.abs(mid[::SUB] - gold[f"resample/{nr}/mid_sub"]).max() <= 1e-6
+    assert np.abs(out[::SUB] - gold[f"resample/{nr}/out_sub"]).max() <= 1e-6
+
+
+def test_resample_length_known_answers():
+    from oracle.augment_oracle import resample_length
+
+    assert resample_length(24000, 16000, 16001) == 24002
+    assert resample_length(24002, 16001, 16000) == 24001
+    assert resample_length(24000, 16000, 15200) == 22800
+    assert resample_length(22800, 15200, 16000) == 24000
+    assert resample_length(48000, 16000, 16000) == 48000
+    assert resample_length(0, 16000, 15999) == 0
+
+
+def test_product_draw_matches_oracle_draw():
+    """The product's host-side decision code must consume python's `random` stream exactly like the reference."""
+    from oracle import augment_oracle as ao
+    from ssr_b200 import augment
+
+    for variant in ("model_training_1", "model_training_01"):
+        for seed in range(40):
+            random.seed(seed)
+            want = ao.draw("random", 16000, variant)
+            tail_want = random.random()
+            random.seed(seed)
+            got = augment.draw_op("random", 16000, variant)
+            tail_got = random.random()
+            assert got.kind == want[0]
+            assert tail_got == tail_want
+            if want[0] == "speed":
+                assert got.new_rate == want[1]["new_rate"]
+            elif want[0] in ("noise", "volume"):
+                assert got.factor == want[1]["factor"]
+            elif want[0] == "pitch":
+                assert got.n_steps == want[1]["n_steps"]
+
+
+def test_length_helpers_match_oracle():
+    """C-ABI length helpers (no GPU needed) against the oracle, including float32-rounding edge cases."""
+    from oracle.augment_oracle import resample_length
+    from ssr_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        n = int(rng.integers(0, 600000))
+        nr = int(rng.integers(14000, 18000))
+        assert lib.ssr_resample_length(n, 16000, nr) == resample_length(n, 16000, nr), (n, nr)
+        assert lib.ssr_resample_length(n, nr, 16000) == resample_length(n, nr, 16000), (n, nr)
+    op = _lib.AugOp(kind=_lib.SSR_AUG_SPEED, new_rate=16001, factor=0.0, reserved=0, seed=0)
+    assert lib.ssr_augment_out_length(op, 24000, 16000) == 24001
+    op.kind = _lib.SSR_AUG_VOLUME
+    assert lib.ssr_augment_out_length(op, 24000, 16000) == 24000

@@ -1,0 +1,109 @@
+"""Generate tests/golden/augment.npz by running the REFERENCE's own augment_audio (imported unmodified from
+/root/reference/model_training_1.py and model_training_01.py) on seeded synthetic clips.
+
+Runs only in the build container. The training scripts import plotting / imbalanced-learn / xgboost packages that
+are not installed here and that augment_audio never touches; they are replaced by empty stub modules for the import.
+
+    python tools/make_golden_aug.py
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden", "augment.npz")
+REF = "/root/reference"
+SUB = 4  # keep every 4th sample of each output (fixture size); length and float64 moments cover the rest
+
+
+class _Anything(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {})
+
+
+def import_reference():
+    for mod in ("matplotlib", "matplotlib.pyplot", "seaborn", "imblearn", "imblearn.over_sampling",
+                "imblearn.pipeline", "xgboost"):
+        if mod not in sys.modules:
+            try:
+                __import__(mod)
+            except Exception:  # noqa: BLE001
+                sys.modules[mod] = _Anything(mod)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="ssr_ref_"))
+    sys.path.insert(0, REF)
+    try:
+        import model_training_1 as v1
+        import model_training_01 as v01
+    finally:
+        os.chdir(cwd)
+    return {"model_training_1": v1, "model_training_01": v01}
+
+
+def cases():
+    """(name, variant, clip index, augmentation_type, seed). Seeds were picked so that 'random' hits every kind."""
+    out = []
+    for variant in ("model_training_1", "model_training_01"):
+        for kind in ("speed", "noise", "volume"):
+            for seed in (0, 1):
+                out.append((f"{variant}/{kind}/{seed}", variant, seed % 3, kind, seed))
+        for seed in range(2, 8):
+            out.append((f"{variant}/random/{seed}", variant, seed % 3, "random", seed))
+    out.append(("model_training_1/none/0", "model_training_1", 1, "none", 0))
+    return out
+
+
+def main():
+    import torch
+
+    from ssr_b200 import synth
+
+    mods = import_reference()
+    clips = synth.aug_clips()
+    fix = {}
+    names = []
+    for name, variant, ci, kind, seed in cases():
+        # peek at what 'random' would pick; the pitch kind (phase vocoder) is not part of this fixture
+        if kind == "random":
+            random.seed(seed)
+            order = {"model_training_1": ["speed", "noise", "volume", "none"],
+                     "model_training_01": ["speed", "noise", "pitch", "volume"]}[variant]
+            if random.choice(order) == "pitch":
+                continue
+        random.seed(seed)
+        torch.manual_seed(seed)
+        out = mods[variant].augment_audio(clips[ci].copy(), augmentation_type=kind)
+        out = np.asarray(out, np.float32)
+        names.append(name)
+        fix[name + "/sub"] = out[::SUB].copy()
+        fix[name + "/len"] = np.int64(out.shape[0])
+        fix[name + "/sum"] = np.float64(out.astype(np.float64).sum())
+        fix[name + "/sumsq"] = np.float64((out.astype(np.float64) ** 2).sum())
+        print(f"  {name}: len {out.shape[0]}  sum {fix[name + '/sum']:.6f}")
+    # one plain Resample round trip at co-prime rates (the 1 GB filter-bank case), straight through torchaudio
+    import torchaudio
+
+    x = torch.from_numpy(clips[0][:24000].copy())[None]
+    for nr in (16001, 15200, 16777):
+        y = torchaudio.transforms.Resample(16000, nr)(x)
+        z = torchaudio.transforms.Resample(nr, 16000)(y)
+        fix[f"resample/{nr}/mid_sub"] = y[0].numpy()[::SUB].copy()
+        fix[f"resample/{nr}/out_sub"] = z[0].numpy()[::SUB].copy()
+        fix[f"resample/{nr}/lens"] = np.array([y.shape[1], z.shape[1]], np.int64)
+        print(f"  resample 16000->{nr}->16000: {y.shape[1]} / {z.shape[1]}")
+    fix["names"] = np.array(names)
+    np.savez_compressed(OUT, **fix)
+    print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
