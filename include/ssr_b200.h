@@ -167,6 +167,34 @@ int ssr_augment(const float* audio_dev, int64_t in_stride, const int32_t* n_in, 
                 int32_t sample_rate, const float* noise_dev, int64_t noise_stride, void* work_dev, int64_t work_bytes,
                 float* out_dev, int64_t out_stride, int32_t* n_out, void* cuda_stream, char* err, int32_t err_len);
 
+/* ---- classifier head on the pooled embeddings, data-parallel training. Engine-independent and
+ * stateless: every buffer is the caller's (device pointers unless noted). New component; what it keeps from the
+ * reference is the Pipeline([StandardScaler, classifier]) / class_weight='balanced' semantics of
+ * /root/reference/model_training_1.py:576-589, :658-680. Model: Linear(D->H) + ReLU + Linear(H->C), class-weighted
+ * softmax cross-entropy, Adam. Flat float32 parameter layout: W1[H,D] | b1[H] | W2[C,H] | b2[C]. */
+int64_t ssr_head_param_count(int32_t D, int32_t H, int32_t C); /* P, or -1 (C <= 32) */
+int64_t ssr_head_work_bytes(int64_t n, int32_t D, int32_t H, int32_t C);
+/* StandardScaler statistics of the local rows, float64 [D]: mean_dev == NULL -> column sums of X;
+ * else column sums of (x - mean)^2. (All-reduce them across ranks, divide by the global row count.) */
+int ssr_head_scaler_stats(const float* X_dev, int64_t n, int32_t D, int64_t ld, const double* mean_dev,
+                          double* out_dev, void* cuda_stream, char* err, int32_t err_len);
+/* Forward + backward over n local rows (rows_dev: optional int32 [n] row gather into X_dev / y_dev; mean/inv_std:
+ * optional fused scaler, float32 [D]). grad_dev: float32 [P + 2], overwritten with the UNNORMALISED sums
+ *   sum_i w_i * dloss_i/dparam | sum_i w_i * loss_i | sum_i w_i      (w_i = class_w_dev[y_i], or 1)
+ * so that one all-reduce(sum) of the buffer gives the global gradient and its normaliser. */
+int ssr_head_grad(const float* X_dev, const int32_t* y_dev, const int32_t* rows_dev, int64_t n, int32_t D, int32_t H,
+                  int32_t C, const float* mean_dev, const float* inv_std_dev, const float* params_dev,
+                  const float* class_w_dev, float* grad_dev, void* work_dev, int64_t work_bytes, void* cuda_stream,
+                  char* err, int32_t err_len);
+/* Adam step (torch.optim.Adam semantics, L2 weight decay) on g = grad[0..P) / grad[P+1]; step counts from 1. */
+int ssr_head_adam(float* params_dev, const float* grad_dev, float* m_dev, float* v_dev, int64_t P, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int32_t step, void* cuda_stream, char* err,
+                  int32_t err_len);
+/* pred_dev int32 [n] (argmax, lowest index on ties) and/or proba_dev float32 [n, C]; work: n * H floats. */
+int ssr_head_predict(const float* X_dev, int64_t n, int32_t D, int32_t H, int32_t C, const float* mean_dev,
+                     const float* inv_std_dev, const float* params_dev, int32_t* pred_dev, float* proba_dev,
+                     void* work_dev, int64_t work_bytes, void* cuda_stream, char* err, int32_t err_len);
+
 /* ---- debug taps: copy a named internal buffer of the last run to host (synchronises). Returns bytes copied,
  * or a negative error. With dst == NULL returns the buffer's size in bytes. `dims` (optional, 4 entries) gets the
  * logical shape, `dtype` (optional) 0 = float32, 1 = bfloat16. */

@@ -63,6 +63,15 @@ SIGNATURES = {
                               c_i32]),
     "ssr_pool_mean": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_cp, c_i32]),
     "ssr_debug_fetch": (c_i64, [c_vp, c_cp, c_vp, c_i64, c_i64p, c_i32p]),
+    "ssr_head_param_count": (c_i64, [c_i32, c_i32, c_i32]),
+    "ssr_head_work_bytes": (c_i64, [c_i64, c_i32, c_i32, c_i32]),
+    "ssr_head_scaler_stats": (c_i32, [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp, c_cp, c_i32]),
+    "ssr_head_grad": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                              c_vp, c_cp, c_i32]),
+    "ssr_head_adam": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                              c_i32, c_vp, c_cp, c_i32]),
+    "ssr_head_predict": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
+                                 c_cp, c_i32]),
     "ssr_resample_length": (c_i32, [c_i32, c_i32, c_i32]),
     "ssr_augment_out_length": (c_i32, [C.POINTER(AugOp), c_i32, c_i32]),
     "ssr_augment_work_bytes": (c_i64, [c_i32p, c_i32, C.POINTER(AugOp), c_i32]),

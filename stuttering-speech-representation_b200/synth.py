@@ -46,6 +46,23 @@ def aug_clips() -> list[np.ndarray]:
     return [a[0], chirp, a[1][:16001]]
 
 
+def cluster_embeddings(n: int, D: int = 1024, n_classes: int = 8, seed: int = 0, spread: float = 5.0,
+                       imbalance: float = 0.6):
+    """BASELINE configs[3] stand-in for pooled embeddings with labels: Gaussian clusters in R^D, geometrically
+    imbalanced class counts, per-feature offsets and scales (so that the StandardScaler matters)."""
+    rng = np.random.default_rng(seed)
+    # the geometry is drawn first, so that it depends on the seed only and not on n
+    centres = rng.standard_normal((n_classes, D)) * spread / np.sqrt(D)
+    offset = rng.standard_normal(D) * 3.0
+    scale = np.exp(rng.standard_normal(D) * 0.5)
+    p = imbalance ** np.arange(n_classes)
+    p /= p.sum()
+    y = rng.choice(n_classes, size=n, p=p)
+    y[:n_classes] = np.arange(n_classes)
+    X = (centres[y] + rng.standard_normal((n, D))) * scale + offset
+    return X.astype(np.float32), y.astype(np.int32)
+
+
 # ------------------------------------------------------------------------------------------------ model configs
 def wavlm_config(name: str):
     from transformers import WavLMConfig
