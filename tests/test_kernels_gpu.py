@@ -199,6 +199,41 @@ def test_attention(slot, H, lens, bias, impl):
         assert err < 2e-2, f"clip {b}: max err {err}"
 
 
+@pytest.mark.parametrize("scale", [1.0, 6.0, 40.0])
+def test_attention_stale_reference_and_rescale(scale):
+    """Non-bias path (Whisper): O accumulates in TMEM against the block-0 reference maximum. Scores that keep rising
+    along the key axis make that reference stale: mildly (probabilities far above 1, no rescale), strongly (partial
+    sums leave the safe range -> in-place rescale of O and redo of the block), and some rows not at all."""
+    lib = _lib()
+    B, slot, H = 2, 700, 2
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(int(scale))
+    qkv = torch.randn(B * slot, 3 * D, device="cuda", generator=g)
+    q = qkv[:, :D].view(B, slot, H, 64)
+    k = qkv[:, D:2 * D].view(B, slot, H, 64)
+    q.mul_(0.05)
+    # key j gets a component along e0 growing with j; queries have +1 / -1 / 0 along e0 depending on the row
+    ramp = torch.linspace(0, 1, slot, device="cuda") * scale * 8
+    k[..., 0] = ramp[None, :, None]
+    sign = torch.tensor([1.0, -1.0, 0.0], device="cuda")[torch.arange(slot, device="cuda") % 3]
+    q[..., 0] = sign[None, :, None]
+    qkv = qkv.bfloat16()
+    lens_t = torch.tensor([slot, 517], device="cuda", dtype=torch.int32)
+    out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
+    e = _err()
+    rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), None, None, 0, 0, 0, None,
+                           e, 512)
+    torch.cuda.synchronize()
+    assert rc == 0, e.value.decode()
+    ref = _attn_ref(qkv, B, slot, H, lens_t, None, None, 0).view(B, slot, D)
+    got = out.float().view(B, slot, D)
+    assert torch.isfinite(got).all()
+    for b in range(B):
+        L = int(lens_t[b])
+        err = (got[b, :L] - ref[b, :L]).abs().max().item()
+        assert err < 2e-2, f"clip {b}: max err {err}"
+
+
 def test_pool_mean():
     lib = _lib()
     B, slot, D = 5, 150, 1024
