@@ -1,0 +1,107 @@
+"""BASELINE configs[4]: N synthetic 3 s clips through WavLM-Large or the Whisper-large encoder, sharded over the GPUs
+of one box (one process per GPU; launch under torchrun for more than one).
+
+    python tools/sweep.py --model wavlm --clips 100000
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29710 \
+        tools/sweep.py --model whisper --clips 100000
+
+Clips are generated ON THE DEVICE by the counter-based generator of the augmentation library (Philox4x32-10 keyed by
+the global clip index: any sharding reproduces the same clip), N(0, 0.1^2) like the BASELINE noise clips. Every rank
+embeds its contiguous index range in batches, keeps the pooled output `[n_local, L+1, D]` on the device, and the
+ranks all-gather the result at the end. Device-timed with CUDA events, max over ranks; prints one
+JSON line with clips/s and a checksum of the gathered tensor (identical at any world size up to batch effects that
+the parity tests bound at 2e-6)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ssr_b200 import WavLMEngine, WhisperEncoderEngine, augment, shard_range, synth  # noqa: E402
+from ssr_b200.augment import AugOp  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="wavlm", choices=["wavlm", "whisper"])
+    ap.add_argument("--clips", type=int, default=100000)
+    ap.add_argument("--batch", type=int, default=0, help="clips per step per GPU (default 256 / 64)")
+    ap.add_argument("--samples", type=int, default=48000)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t0 = time.time()
+    if a.model == "wavlm":
+        model, fe = synth.build_wavlm("large")
+        eng = WavLMEngine.from_hf(model, fe, device=local)
+        batch = a.batch or 256
+    else:
+        model, fe = synth.build_whisper_encoder("large")
+        eng = WhisperEncoderEngine.from_hf(model, fe, device=local)
+        batch = a.batch or 64
+    del model
+    build_s = time.time() - t0
+    aug = augment.get_augmenter(local)
+    lo, hi = shard_range(a.clips, rank, world)
+    n_local = hi - lo
+    L1, D = eng.layers + 1, eng.hidden
+    pooled = torch.empty((n_local, L1, D), dtype=torch.float32, device="cuda")
+    zeros = torch.zeros((batch, a.samples), dtype=torch.float32, device="cuda")
+    clips = torch.empty((batch, a.samples + 8), dtype=torch.float32, device="cuda")
+    n = [a.samples] * batch
+
+    def step(b0, b1):
+        ops = [AugOp("noise", factor=0.1, seed=i) for i in range(b0, b1)]
+        y, n_out = aug.run_device(zeros[: b1 - b0], n[: b1 - b0], ops, out=clips[: b1 - b0])
+        eng.pooled_device(y, n_out, out=pooled[b0 - lo:b1 - lo])
+
+    step(lo, min(lo + batch, hi))  # warm-up (workspace growth, first-launch costs)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for b0 in range(lo, hi, batch):
+        step(b0, min(b0 + batch, hi))
+    if world > 1:  # final all-gather of the pooled embeddings, inside the timed region
+        sizes = [shard_range(a.clips, r, world) for r in range(world)]
+        mx = max(h - l for l, h in sizes)
+        pad = torch.zeros((mx, L1, D), dtype=torch.float32, device="cuda")
+        pad[:n_local] = pooled
+        full = torch.empty((world * mx, L1, D), dtype=torch.float32, device="cuda") if rank == 0 else None
+        dist.gather(pad, [full[r * mx:(r + 1) * mx] for r in range(world)] if rank == 0 else None, dst=0)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        if world > 1:
+            parts = [full[r * mx: r * mx + (h - l)] for r, (l, h) in enumerate(sizes)]
+            allp = torch.cat(parts)
+        else:
+            allp = pooled
+        assert allp.shape[0] == a.clips and bool(torch.isfinite(allp).all())
+        out = {"workload": f"{a.model} sweep, {a.clips} clips x {a.samples} samples, batch {batch}/GPU, clips generated "
+                           "on the device (Philox keyed by clip index)",
+               "n_gpus": world, "clips": a.clips, "seconds": round(ms.item() / 1e3, 3),
+               "clips_per_s": round(a.clips / ms.item() * 1e3, 1), "engine_build_s": round(build_s, 1),
+               "gathered_bytes": int(allp.numel() * 4),
+               "checksum": float(allp.double().abs().mean().item()),
+               "first_clip_layer_last_norm": float(allp[0, -1].norm().item())}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
