@@ -5,15 +5,25 @@
 // With one query token per clip the cross-attention is re-associated so that the encoder states are never projected:
 //     scores[h, j] = q_h . (Wk_h enc_j)          = (Wk_h^T q_h) . enc_j        =: q'_h . enc_j
 //     out_h        = sum_j p[h, j] (Wv_h enc_j + bv_h) = Wv_h (sum_j p[h, j] enc_j) + bv_h
-// i.e. two HBM-bound passes over enc [1500, D] per clip and layer (~0.16 GFLOP) instead of the K / V projections of
-// all 1500 positions (9.8 GFLOP per clip and layer in the reference). The token-level Linear layers (M = batch rows)
-// reuse the tcgen05 GEMM. These kernels are the small fp32 CUDA-core pieces in between.
+// i.e. attention of H query vectors of width D against K = V = enc [1500, D] (~0.16 GFLOP per clip and layer)
+// instead of the K / V projections of all 1500 positions (9.8 GFLOP per clip and layer in the reference).
+//
+// dec_xattn_kernel does scores, softmax and the weighted sum in ONE pass over enc (HBM-bound: 3.84 MB per clip and
+// layer, read once): 16-row chunks of enc stream through a 3-stage TMA ring (128B-swizzled boxes); per chunk the
+// 16 warps split D for S = E Q' (mma.sync m16n8k16, bf16, fp32 accumulate; partials reduced through shared memory in
+// fixed order), an online softmax over the chunk updates the running max / sum per head, and ctx^T[d, h] += E^T P is
+// accumulated in registers (A operand = the same shared-memory tile through ldmatrix.trans). A clip's rows are split
+// over a few CTAs (so that the grid covers the SMs); dec_vproj_kernel merges the splits and applies Wv, bv.
+// The token-level Linear layers (M = batch rows) reuse the tcgen05 GEMM.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace ssr {
 
 namespace {
+
+using namespace ptx;
 
 // h[b, :] = v[:]  (decoder hidden_states[0] = embed_tokens[0] + embed_positions[0], identical for every clip)
 __global__ void bcast_rows_kernel(const float* __restrict__ v, float* __restrict__ out, int D, long long ld) {
@@ -37,126 +47,257 @@ dec_qproj_kernel(const float* __restrict__ q, const bf16* __restrict__ wk, float
   }
 }
 
-// scores[b, h, j] = enc[b, j, :] . q'[b, h, :]   ; a warp owns 4 encoder rows, q' of the clip sits in shared memory.
-constexpr int SC_ROWS = 32;  // rows per block (8 warps x 4)
-template <int HMAX>
-__global__ void __launch_bounds__(256)
-dec_scores_kernel(const bf16* __restrict__ enc, const float* __restrict__ qp, float* __restrict__ scores, int T, int D,
-                  int H) {
-  extern __shared__ float qsm[];  // [H][D]
-  const int b = blockIdx.y;
-  const int j0 = blockIdx.x * SC_ROWS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < H * D; i += 256) qsm[i] = qp[(long long)b * H * D + i];
+// ------------------------------------------------------------------------------------------------ fused pass
+constexpr int XC_ROWS = 16;    // encoder rows per chunk (= MMA M of the score GEMM, K of the context GEMM)
+constexpr int XC_STAGES = 3;
+constexpr int XC_WARPS = 16;
+constexpr int XC_THREADS = XC_WARPS * 32;
+constexpr int XC_HP = 24;      // heads padded to three n8 tiles
+constexpr int XC_PP = 36;      // byte pitch of a P^T row ([h][16 t] bf16)
+constexpr int XC_BOX = XC_ROWS * 128;  // one TMA box: 16 rows x 64 bf16
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct XattnSmem {
+  // byte offsets inside dynamic shared memory for a given D
+  int stage, qs, red, ps, misc, total, qpitch;
+  __host__ __device__ explicit XattnSmem(int D) {
+    stage = 0;
+    const int stage_bytes = (D / 64) * XC_BOX;
+    qpitch = D * 2 + 16;
+    qs = XC_STAGES * stage_bytes;
+    red = qs + XC_HP * qpitch;
+    ps = red + XC_WARPS * XC_ROWS * XC_HP * 4;
+    misc = ps + ((XC_HP * XC_PP + 15) & ~15);
+    total = misc + 512;
+  }
+};
+
+// grid = (S, B): CTA (s, b) owns encoder rows [s*R, min(T, (s+1)*R)) of clip b, R a multiple of 16.
+// part[(b*S + s)][h][d] = sum_j exp(score_j - m) enc[j, d]; ml[(b*S + s)][h] = (m, l).
+template <int MT>  // D = 256 * MT: each warp owns 16*MT columns of enc
+__global__ void __launch_bounds__(XC_THREADS, 1)
+dec_xattn_kernel(const __grid_constant__ CUtensorMap tme, const float* __restrict__ qp, float* __restrict__ part,
+                 float* __restrict__ ml, int T, int H, int R) {
+  constexpr int D = 256 * MT;
+  constexpr int W = 16 * MT;
+  constexpr int STAGE_BYTES = (D / 64) * XC_BOX;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const XattnSmem L(D);
+  uint8_t* qs = smem + L.qs;
+  float* red = reinterpret_cast<float*>(smem + L.red);
+  uint8_t* ps = smem + L.ps;
+  float* m_run = reinterpret_cast<float*>(smem + L.misc);
+  float* l_run = m_run + XC_HP;
+  float* alpha_s = l_run + XC_HP;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L.misc + 3 * XC_HP * 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int s = blockIdx.x, S = gridDim.x, b = blockIdx.y;
+  const int t_begin = s * R, t_end = min(T, t_begin + R);
+  const int n_chunks = t_end > t_begin ? (t_end - t_begin + XC_ROWS - 1) / XC_ROWS : 0;
+  const long long row_base = (long long)b * T + t_begin;
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023) __trap();
+    prefetch_tmap(&tme);
+    for (int i = 0; i < XC_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  // q' of this clip -> bf16 [24][D] (padding heads zero), running statistics
+  for (int i = tid; i < XC_HP * D; i += XC_THREADS) {
+    const int h = i / D, d = i - h * D;
+    const float v = h < H ? qp[((long long)b * H + h) * D + d] : 0.f;
+    *reinterpret_cast<bf16*>(qs + h * L.qpitch + d * 2) = __float2bfloat16_rn(v);
+  }
+  if (tid < XC_HP) {
+    m_run[tid] = -INFINITY;
+    l_run[tid] = 0.f;
+  }
   __syncthreads();
-  float acc[4][HMAX];
+
+  auto issue = [&](int chunk) {  // one thread: all boxes of a chunk into stage chunk % XC_STAGES
+    const int st = chunk % XC_STAGES;
+    mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+    for (int kb = 0; kb < D / 64; ++kb)
+      tma_load_2d(smem + st * STAGE_BYTES + kb * XC_BOX, &tme, &full[st], kb * 64,
+                  (int)(row_base + (long long)chunk * XC_ROWS));
+  };
+  if (tid == 0)
+    for (int i = 0; i < XC_STAGES && i < n_chunks; ++i) issue(i);
+
+  float acc[MT][3][4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-    for (int h = 0; h < HMAX; ++h) acc[r][h] = 0.f;
-  const int jr = j0 + warp * 4;
-  const bf16* e0 = enc + ((long long)b * T + jr) * D;
-  for (int d = lane; d < D; d += 32) {
-    float ev[4];
+    for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) ev[r] = (jr + r < T) ? __bfloat162float(e0[(long long)r * D + d]) : 0.f;
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int st = ch % XC_STAGES;
+    const uint32_t stage_addr = smem_u32(smem + st * STAGE_BYTES);
+    mbar_wait(&full[st], (ch / XC_STAGES) & 1);
+
+    // ---- phase 1: partial scores over this warp's columns: S[t, h] += E[t, d] q'[h, d]
+    float sc[3][4];
 #pragma unroll
-    for (int h = 0; h < HMAX; ++h) {
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[nt][i] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < MT; ++ks) {
+      const int k0 = warp * W + ks * 16;
+      const int row = lane & 15;
+      const int kc = ((k0 & 63) >> 3) + (lane >> 4);
+      uint32_t a[4];
+      ldmatrix_x4(stage_addr + (k0 >> 6) * XC_BOX + row * 128 + ((kc ^ (row & 7)) << 4), a);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const uint8_t* qrow = qs + (nt * 8 + g) * L.qpitch + (k0 + 2 * c) * 2;
+        mma_bf16_16816(sc[nt], a, *reinterpret_cast<const uint32_t*>(qrow),
+                       *reinterpret_cast<const uint32_t*>(qrow + 16));
+      }
+    }
+    {
+      float* r = red + warp * (XC_ROWS * XC_HP);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        const int h = nt * 8 + 2 * c;
+        r[g * XC_HP + h] = sc[nt][0];
+        r[g * XC_HP + h + 1] = sc[nt][1];
+        r[(g + 8) * XC_HP + h] = sc[nt][2];
+        r[(g + 8) * XC_HP + h + 1] = sc[nt][3];
+      }
+    }
+    __syncthreads();  // (A) partial scores visible; every warp has finished phase 2 of the previous chunk
+    if (tid == 0 && ch >= 1 && ch - 1 + XC_STAGES < n_chunks) issue(ch - 1 + XC_STAGES);  // refill the freed stage
+
+    // ---- online softmax over the chunk: thread (h, t) with h = tid / 16, t = tid % 16 (a half-warp per head)
+    if (tid < XC_HP * XC_ROWS) {
+      const int h = tid >> 4, t = tid & 15;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < XC_WARPS; ++w) v += red[w * (XC_ROWS * XC_HP) + t * XC_HP + h];
+      const bool valid = t_begin + ch * XC_ROWS + t < t_end;
+      v = valid ? v : -INFINITY;
+      float cm = v;
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+      const float m_old = m_run[h];
+      const float m_new = fmaxf(m_old, cm);  // finite: every chunk holds at least one valid row
+      const float p = valid ? __expf(v - m_new) : 0.f;
+      float ls = p;
+#pragma unroll
+      for (int o = 8; o >= 1; o >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+      *reinterpret_cast<bf16*>(ps + h * XC_PP + t * 2) = __float2bfloat16_rn(p);
+      __syncwarp();
+      if (t == 0) {
+        const float al = __expf(m_old - m_new);  // 0 on the first chunk (m_old = -inf)
+        alpha_s[h] = al;
+        m_run[h] = m_new;
+        l_run[h] = l_run[h] * al + ls;
+      }
+    }
+    __syncthreads();  // (B) P^T and alpha visible
+
+    // ---- phase 2: ctx^T[d, h] = alpha_h * ctx^T[d, h] + sum_t E[t, d] P[t, h]
+    uint32_t pb[3][2];
+    float al[3][2];
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      const uint8_t* prow = ps + (nt * 8 + g) * XC_PP + (2 * c) * 2;
+      pb[nt][0] = *reinterpret_cast<const uint32_t*>(prow);
+      pb[nt][1] = *reinterpret_cast<const uint32_t*>(prow + 16);
+      al[nt][0] = alpha_s[nt * 8 + 2 * c];
+      al[nt][1] = alpha_s[nt * 8 + 2 * c + 1];
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int d0 = warp * W + mt * 16;
+      const int mat = lane >> 3, r = lane & 7;
+      const int trow = r + ((mat & 2) ? 8 : 0);
+      const int dc = ((d0 & 63) >> 3) + (mat & 1);
+      uint32_t a[4];
+      ldmatrix_x4_trans(stage_addr + (d0 >> 6) * XC_BOX + trow * 128 + ((dc ^ (trow & 7)) << 4), a);
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) {
+        acc[mt][nt][0] *= al[nt][0];
+        acc[mt][nt][1] *= al[nt][1];
+        acc[mt][nt][2] *= al[nt][0];
+        acc[mt][nt][3] *= al[nt][1];
+        mma_bf16_16816(acc[mt][nt], a, pb[nt][0], pb[nt][1]);
+      }
+    }
+  }
+
+  // ---- partial results of this split
+  const long long slot = (long long)b * S + s;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int d = warp * W + mt * 16 + g;
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt) {
+      const int h = nt * 8 + 2 * c;
+      float* p0 = part + (slot * H + h) * D + d;
       if (h < H) {
-        const float w = qsm[h * D + d];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r][h] = fmaf(ev[r], w, acc[r][h]);
+        p0[0] = acc[mt][nt][0];
+        p0[8] = acc[mt][nt][2];
+      }
+      if (h + 1 < H) {
+        p0[D] = acc[mt][nt][1];
+        p0[D + 8] = acc[mt][nt][3];
       }
     }
   }
-#pragma unroll
-  for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int h = 0; h < HMAX; ++h) {
-      float v = acc[r][h];
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && h < H && jr + r < T) scores[((long long)b * H + h) * T + jr + r] = v;
-    }
-}
-
-// in-place softmax over j for every (clip, head)
-__global__ void __launch_bounds__(256)
-dec_softmax_kernel(float* __restrict__ s, int T) {
-  __shared__ float red[8];
-  float* row = s + (long long)blockIdx.x * T;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float m = -INFINITY;
-  for (int j = threadIdx.x; j < T; j += 256) m = fmaxf(m, row[j]);
-  for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if (lane == 0) red[warp] = m;
   __syncthreads();
-  m = red[0];
-  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-  __syncthreads();
-  float l = 0.f;
-  for (int j = threadIdx.x; j < T; j += 256) {
-    const float p = expf(row[j] - m);
-    row[j] = p;
-    l += p;
-  }
-  for (int o = 16; o >= 1; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-  if (lane == 0) red[warp] = l;
-  __syncthreads();
-  l = 0.f;
-  for (int i = 0; i < 8; ++i) l += red[i];
-  const float inv = 1.0f / l;
-  for (int j = threadIdx.x; j < T; j += 256) row[j] *= inv;
-}
-
-// ctx_part[seg, b, h, d] = sum_{j in segment} p[b, h, j] * enc[b, j, d] ; a thread owns one column d and all heads.
-constexpr int CTX_SEGS = 4;
-template <int HMAX>
-__global__ void __launch_bounds__(256)
-dec_ctx_kernel(const bf16* __restrict__ enc, const float* __restrict__ p, float* __restrict__ part, int T, int D, int H,
-               int B) {
-  __shared__ float ps[HMAX][64];
-  const int b = blockIdx.z, seg = blockIdx.y;
-  const int d = blockIdx.x * 256 + threadIdx.x;
-  const int seg_len = (T + CTX_SEGS - 1) / CTX_SEGS;
-  const int ja = seg * seg_len, jb = min(T, ja + seg_len);
-  float acc[HMAX];
-#pragma unroll
-  for (int h = 0; h < HMAX; ++h) acc[h] = 0.f;
-  for (int j0 = ja; j0 < jb; j0 += 64) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < H * 64; i += 256) {
-      const int h = i >> 6, jj = i & 63;
-      ps[h][jj] = (j0 + jj < jb) ? p[((long long)b * H + h) * T + j0 + jj] : 0.f;
-    }
-    __syncthreads();
-    if (d < D) {
-      const int n = min(64, jb - j0);
-      for (int jj = 0; jj < n; ++jj) {
-        const float e = __bfloat162float(enc[((long long)b * T + j0 + jj) * D + d]);
-#pragma unroll
-        for (int h = 0; h < HMAX; ++h)
-          if (h < H) acc[h] = fmaf(ps[h][jj], e, acc[h]);
-      }
-    }
-  }
-  if (d < D) {
-#pragma unroll
-    for (int h = 0; h < HMAX; ++h)
-      if (h < H) part[(((long long)seg * B + b) * H + h) * D + d] = acc[h];
+  if (tid < H) {
+    ml[(slot * H + tid) * 2] = m_run[tid];
+    ml[(slot * H + tid) * 2 + 1] = l_run[tid];
   }
 }
 
-// cv[b, h*64 + e] = Wv[h*64 + e, :] . (sum_seg ctx_part[seg, b, h, :]) + bv[h*64 + e]   -> bf16 (next GEMM's A operand)
+// cv[b, h*64 + e] = Wv[h*64 + e, :] . ctx[b, h, :] + bv[h*64 + e]  -> bf16 (next GEMM's A operand), where ctx merges
+// the S splits: ctx = sum_s exp(m_s - M) part_s / sum_s exp(m_s - M) l_s.
 __global__ void __launch_bounds__(256)
-dec_vproj_kernel(const float* __restrict__ part, const bf16* __restrict__ wv, const float* __restrict__ bv,
-                 bf16* __restrict__ out, int D, int B) {
-  extern __shared__ float ctx[];  // [D]
+dec_vproj_kernel(const float* __restrict__ part, const float* __restrict__ ml, int S, const bf16* __restrict__ wv,
+                 const float* __restrict__ bv, bf16* __restrict__ out, int D) {
+  extern __shared__ float ctx[];  // [D] + weights [S]
+  float* wgt = ctx + D;
   const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
+  if (threadIdx.x == 0) {
+    float M = -INFINITY;
+    for (int s = 0; s < S; ++s) M = fmaxf(M, ml[(((long long)b * S + s) * H + h) * 2]);
+    float Lsum = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float* e = ml + (((long long)b * S + s) * H + h) * 2;
+      const float w = e[1] > 0.f ? __expf(e[0] - M) : 0.f;  // an empty split has l = 0, m = -inf
+      wgt[s] = w;
+      Lsum += w * e[1];
+    }
+    const float inv = 1.0f / Lsum;
+    for (int s = 0; s < S; ++s) wgt[s] *= inv;
+  }
+  __syncthreads();
   for (int d = threadIdx.x; d < D; d += 256) {
-    float s = 0.f;
-    for (int seg = 0; seg < CTX_SEGS; ++seg) s += part[(((long long)seg * B + b) * H + h) * D + d];
-    ctx[d] = s;
+    float v = 0.f;
+    for (int s = 0; s < S; ++s)
+      if (wgt[s] != 0.f) v = fmaf(wgt[s], part[(((long long)b * S + s) * H + h) * D + d], v);
+    ctx[d] = v;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -167,6 +308,22 @@ dec_vproj_kernel(const float* __restrict__ part, const bf16* __restrict__ wv, co
     for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) out[(long long)b * D + h * 64 + e] = __float2bfloat16_rn(acc + bv[h * 64 + e]);
   }
+}
+
+template <int MT>
+int launch_xattn(const CUtensorMap& tme, const DecCrossArgs& a, int S, int R, cudaStream_t st, std::string& err) {
+  const XattnSmem L(256 * MT);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(dec_xattn_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    if (ce != cudaSuccess) {
+      err = std::string("cudaFuncSetAttribute(dec_xattn_kernel): ") + cudaGetErrorString(ce);
+      return -1;
+    }
+    attr_set = true;
+  }
+  dec_xattn_kernel<MT><<<dim3(S, a.B), XC_THREADS, L.total, st>>>(tme, a.qp, a.ctx_part, a.ml, a.T, a.H, R);
+  return 0;
 }
 
 }  // namespace
@@ -182,27 +339,41 @@ int launch_bcast_rows(const float* v, float* out, int B, int D, long long ld, cu
   return 0;
 }
 
+int dec_cross_splits(int B, int T, int num_sms) {
+  int S = num_sms / (B > 0 ? B : 1);
+  const int max_s = ceil_div(T, 4 * XC_ROWS);  // at least 4 chunks per split
+  if (S > max_s) S = max_s;
+  return S < 1 ? 1 : S;
+}
+
 int launch_dec_cross_attention(const DecCrossArgs& a, cudaStream_t st, std::string& err) {
-  if (a.H > 20 || a.D != a.H * 64) {
-    err = "decoder cross-attention: supports head_dim 64 and at most 20 heads";
+  if (a.H > 20 || a.D != a.H * 64 || a.D % 256 != 0 || a.D > 1280) {
+    err = "decoder cross-attention: supports head_dim 64, at most 20 heads, d_model a multiple of 256";
     return -1;
   }
-  static bool attr_set = false;
-  const int sc_smem = a.H * a.D * 4;
-  if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(dec_scores_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * 1280 * 4);
-    if (ce != cudaSuccess) {
-      err = std::string("cudaFuncSetAttribute(dec_scores_kernel): ") + cudaGetErrorString(ce);
-      return -1;
-    }
-    attr_set = true;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
+  const int S = dec_cross_splits(a.B, a.T, num_sms);
+  const int R = ceil_div(ceil_div(a.T, S), XC_ROWS) * XC_ROWS;
+  CUtensorMap tme;
+  if (make_tmap_2d(&tme, a.enc, (unsigned long long)a.D, (unsigned long long)a.B * a.T, (unsigned long long)a.D,
+                   XC_ROWS, err))
+    return -1;
   dec_qproj_kernel<<<dim3(a.H, a.B), 256, 0, st>>>(a.q, a.wk, a.qp, a.D);
-  dec_scores_kernel<20><<<dim3(ceil_div(a.T, SC_ROWS), a.B), 256, sc_smem, st>>>(a.enc, a.qp, a.scores, a.T, a.D, a.H);
-  dec_softmax_kernel<<<a.B * a.H, 256, 0, st>>>(a.scores, a.T);
-  dec_ctx_kernel<20><<<dim3(ceil_div(a.D, 256), CTX_SEGS, a.B), 256, 0, st>>>(a.enc, a.scores, a.ctx_part, a.T, a.D,
-                                                                             a.H, a.B);
-  dec_vproj_kernel<<<dim3(a.H, a.B), 256, a.D * 4, st>>>(a.ctx_part, a.wv, a.bv, a.out, a.D, a.B);
+  int rc = 0;
+  switch (a.D / 256) {
+    case 1: rc = launch_xattn<1>(tme, a, S, R, st, err); break;
+    case 2: rc = launch_xattn<2>(tme, a, S, R, st, err); break;
+    case 3: rc = launch_xattn<3>(tme, a, S, R, st, err); break;
+    case 4: rc = launch_xattn<4>(tme, a, S, R, st, err); break;
+    default: rc = launch_xattn<5>(tme, a, S, R, st, err); break;
+  }
+  if (rc) return rc;
+  dec_vproj_kernel<<<dim3(a.H, a.B), 256, (a.D + S) * 4, st>>>(a.ctx_part, a.ml, S, a.wv, a.bv, a.out, a.D);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("decoder cross-attention launch: ") + cudaGetErrorString(ce);

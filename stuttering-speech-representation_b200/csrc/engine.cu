@@ -1081,8 +1081,9 @@ int whisper_decoder_token(ssr_engine* e, int B, float* dec_out, cudaStream_t st)
   if (e->dec_t1.ensure((size_t)B * D * 2, st, err)) return -1;
   if (e->dec_q.ensure((size_t)B * D * 4, st, err)) return -1;
   if (e->dec_qp.ensure((size_t)B * H * D * 4, st, err)) return -1;
-  if (e->dec_scores.ensure((size_t)B * H * T * 4, st, err)) return -1;
-  if (e->dec_ctx.ensure((size_t)4 * B * H * D * 4, st, err)) return -1;
+  // row splits per clip never exceed max(1, #SMs / B): (B + 256) slots cover every batch size
+  if (e->dec_scores.ensure((size_t)(B + 256) * H * 2 * 4, st, err)) return -1;
+  if (e->dec_ctx.ensure((size_t)(B + 256) * H * D * 4, st, err)) return -1;
   if (e->dec_cv.ensure((size_t)B * D * 2, st, err)) return -1;
   if (e->dec_mid.ensure((size_t)B * Fd * 2, st, err)) return -1;
   float* h = e->dec_h.as<float>();
@@ -1140,14 +1141,14 @@ int whisper_decoder_token(ssr_engine* e, int B, float* dec_out, cudaStream_t st)
       a.bv = W.b_cv;
       a.enc = e->xn.as<bf16>();
       a.qp = e->dec_qp.as<float>();
-      a.scores = e->dec_scores.as<float>();
+      a.ml = e->dec_scores.as<float>();
       a.ctx_part = e->dec_ctx.as<float>();
       a.out = cv;
       a.B = B;
       a.T = T;
       a.D = D;
       a.H = H;
-      e->launches += 5;
+      e->launches += 3;
       ProfScope ps(e, st, "dec_cross_attention", 4.0 * (double)B * H * T * D);
       if (launch_dec_cross_attention(a, st, err)) return -1;
     }

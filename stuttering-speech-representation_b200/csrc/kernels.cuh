@@ -60,12 +60,13 @@ struct DecCrossArgs {
   const float* bv;    // [D]
   const bf16* enc;    // [B * T, D] encoder last_hidden_state (bf16 copy)
   float* qp;          // scratch [B, H, D]
-  float* scores;      // scratch [B, H, T]
-  float* ctx_part;    // scratch [4, B, H, D]
+  float* ml;          // scratch [B, S, H, 2]  running max / sum of each row split (S = dec_cross_splits)
+  float* ctx_part;    // scratch [B, S, H, D]
   bf16* out;          // [B, D] attention output before out_proj (bf16: next GEMM's A operand)
   int B, T, D, H;
 };
 int launch_dec_cross_attention(const DecCrossArgs& a, cudaStream_t st, std::string& err);
+int dec_cross_splits(int B, int T, int num_sms);  // row splits per clip (scratch sizing)
 int launch_bcast_rows(const float* v, float* out, int B, int D, long long ld, cudaStream_t st, std::string& err);
 
 // WavLM waveform statistics + first conv layer (C_in = 1, k = 10, stride 5) fused with its normalisation + GELU.
