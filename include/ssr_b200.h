@@ -138,15 +138,17 @@ int ssr_pool_mean(const float* x, int32_t B, int32_t slot, int32_t D, const int3
 
 /* ---- waveform augmentation, batched on the device. Engine-independent.
  * Replaces augment_audio of /root/reference/model_training_1.py:166-213 and model_training_01.py:140-192 (kinds
- * speed / noise / volume / none; the decision which kind and which factor stays on the host, drawn exactly like the
+ * speed / noise / volume / pitch / none; the decision which kind and which factor stays on the host, drawn exactly like the
  * reference draws it, see stuttering-speech-representation_b200/augment.py). The speed kind is torchaudio's
  * Resample(sr -> new_rate) followed by Resample(new_rate -> sr) (sinc_interp_hann, width 6, rolloff 0.99); every
- * kind ends with clamp(-1, 1) (model_training_1.py:204). */
-enum { SSR_AUG_NONE = 0, SSR_AUG_SPEED = 1, SSR_AUG_NOISE = 2, SSR_AUG_VOLUME = 3 };
+ * kind ends with clamp(-1, 1) (model_training_1.py:204). The pitch kind is torchaudio's PitchShift(sr, n_steps):
+ * STFT 512/128 -> phase vocoder -> inverse STFT -> float32-kernel resample -> crop / pad to the input length
+ * (model_training_01.py:174-178); it needs more than 256 samples. */
+enum { SSR_AUG_NONE = 0, SSR_AUG_SPEED = 1, SSR_AUG_NOISE = 2, SSR_AUG_VOLUME = 3, SSR_AUG_PITCH = 4 };
 
 typedef struct ssr_aug_op {
   int32_t kind;     /* SSR_AUG_* */
-  int32_t new_rate; /* speed: int(sample_rate * speed_factor), model_training_1.py:185 */
+  int32_t new_rate; /* speed: int(sample_rate * speed_factor), model_training_1.py:185; pitch: n_steps */
   float factor;     /* noise: noise_factor; volume: volume_factor */
   int32_t reserved;
   uint64_t seed;    /* noise without caller-supplied normals: key of the counter-based generator */

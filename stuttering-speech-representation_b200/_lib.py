@@ -29,7 +29,7 @@ class Weight(C.Structure):
     _fields_ = [("name", c_cp), ("data", c_vp), ("numel", c_i64)]
 
 
-SSR_AUG_NONE, SSR_AUG_SPEED, SSR_AUG_NOISE, SSR_AUG_VOLUME = 0, 1, 2, 3
+SSR_AUG_NONE, SSR_AUG_SPEED, SSR_AUG_NOISE, SSR_AUG_VOLUME, SSR_AUG_PITCH = 0, 1, 2, 3, 4
 
 
 class AugOp(C.Structure):

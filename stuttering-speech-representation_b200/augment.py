@@ -15,8 +15,9 @@ batched, and its output stays on the device for the encoder — the reference in
 kind draws its normals with `torch.randn_like` on the CPU generator, like the reference, so that output is
 bit-identical under the same seeds; the batched API defaults to the device generator (Philox, keyed by clip).
 
-Not built: the `pitch` kind of model_training_01 (torchaudio PitchShift = phase vocoder + resample). `draw_op`
-consumes its random draw for stream compatibility, and the clip is passed through unchanged with a warning.
+The `pitch` kind of model_training_01 (torchaudio PitchShift: STFT -> phase vocoder -> inverse STFT -> resample) is
+built as well; being a phase vocoder its output is only statistically reproducible on tonal input (the reference's own
+output moves at the percent level with FFT rounding), see csrc/augment.cu.
 """
 from __future__ import annotations
 
@@ -41,7 +42,7 @@ VARIANTS = {
                           "noise": (0.005, 0.02), "volume": (0.8, 1.2)},
 }
 _KIND_CODE = {"none": _lib.SSR_AUG_NONE, "speed": _lib.SSR_AUG_SPEED, "noise": _lib.SSR_AUG_NOISE,
-              "volume": _lib.SSR_AUG_VOLUME, "pitch": _lib.SSR_AUG_NONE}
+              "volume": _lib.SSR_AUG_VOLUME, "pitch": _lib.SSR_AUG_PITCH}
 
 
 @dataclass
@@ -72,7 +73,8 @@ def draw_op(augmentation_type="random", sample_rate=16000, variant="model_traini
 
 
 def out_length(op: AugOp, n: int, sample_rate=16000) -> int:
-    c = _lib.AugOp(kind=_KIND_CODE[op.kind], new_rate=op.new_rate, factor=op.factor, reserved=0, seed=op.seed)
+    c = _lib.AugOp(kind=_KIND_CODE[op.kind], new_rate=op.n_steps if op.kind == "pitch" else op.new_rate,
+                   factor=op.factor, reserved=0, seed=op.seed)
     return int(_lib.load().ssr_augment_out_length(C.byref(c), int(n), int(sample_rate)))
 
 
@@ -91,10 +93,9 @@ class Augmenter:
     def _c_ops(self, ops: Sequence[AugOp]):
         arr = (_lib.AugOp * len(ops))()
         for i, op in enumerate(ops):
-            if op.kind == "pitch" and op.n_steps != 0:
-                logger.warning("pitch augmentation is not built; clip passed through unchanged")
-            arr[i] = _lib.AugOp(kind=_KIND_CODE[op.kind], new_rate=int(op.new_rate), factor=float(op.factor),
-                                reserved=0, seed=int(op.seed) & 0xFFFFFFFFFFFFFFFF)
+            arr[i] = _lib.AugOp(kind=_KIND_CODE[op.kind],
+                                new_rate=int(op.n_steps if op.kind == "pitch" else op.new_rate),
+                                factor=float(op.factor), reserved=0, seed=int(op.seed) & 0xFFFFFFFFFFFFFFFF)
         return arr
 
     def run_device(self, audio: torch.Tensor, n_samples, ops: Sequence[AugOp], noise: torch.Tensor | None = None,

@@ -35,9 +35,14 @@ struct AugClip {
   int n_in;       // samples in
   int n_mid;      // speed: length after the first resample
   int n_out;      // samples out
-  int o1, n1;     // first pass: reduced orig / new rate
+  int o1, n1;     // speed: reduced orig / new rate of the first pass. pitch: reduced int(sr / rate) and sr
   float factor;   // noise std / gain
   unsigned long long seed;
+  // pitch shift only
+  double rate;             // 2 ** (-n_steps / 12)
+  int frames, frames2;     // STFT frames before / after the phase vocoder
+  int n_res;               // length after the final resample (before crop / pad to n_in)
+  long long spec_off, spec2_off, y_off;  // float offsets into the pitch scratch area
 };
 
 // ------------------------------------------------------------------------------------------------ sinc resampler
@@ -90,6 +95,167 @@ __device__ __forceinline__ float resample_one(const float* __restrict__ x, int n
     cw = cw2;
   }
   return acc;
+}
+
+// The same resampler with the filter bank evaluated in FLOAT32 throughout, operation for operation as torchaudio
+// does when `_get_sinc_resample_kernel` is given dtype=float32 — which is what transforms.PitchShift does
+// (initialize_parameters passes dtype=input.dtype). No fused multiply-adds in the tap weight.
+__device__ __forceinline__ float resample_one_f32(const float* __restrict__ x, int n_in, int o, int nw, long long n) {
+  const long long q = n / nw;
+  const int p = (int)(n - q * nw);
+  const double based = (double)(o < nw ? o : nw) * 0.99;
+  const float base = (float)based;
+  const float scale = (float)(based / (double)o);
+  const float pi = 3.14159274101257324f;
+  const float phase = __fdiv_rn(-(float)p, (float)nw);
+  const double half = 6.0 * (double)o / based;
+  const double centre = (double)((long long)p * o) / (double)nw;
+  long long m_lo = (long long)floor(centre - half) - 2;
+  long long m_hi = (long long)ceil(centre + half) + 2;
+  const long long base_idx = q * o;
+  if (base_idx + m_lo < 0) m_lo = -base_idx;
+  if (base_idx + m_hi > (long long)n_in - 1) m_hi = (long long)n_in - 1 - base_idx;
+  float acc = 0.f;
+  for (long long m = m_lo; m <= m_hi; ++m) {
+    const float t = __fmul_rn(__fadd_rn(phase, __fdiv_rn((float)m, (float)o)), base);
+    if (fabsf(t) < 6.0f) {
+      const float cw = cosf(__fdiv_rn(__fdiv_rn(__fmul_rn(t, pi), 6.0f), 2.0f));
+      const float window = __fmul_rn(cw, cw);
+      const float tp = __fmul_rn(t, pi);
+      const float sinc = tp == 0.f ? 1.0f : __fdiv_rn(sinf(tp), tp);
+      const float h = __fmul_rn(sinc, __fmul_rn(window, scale));
+      acc = fmaf(x[base_idx + m], h, acc);
+    }
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ pitch shift
+// torchaudio.transforms.PitchShift(sr, n_steps) (REF/model_training_01.py:174-178): STFT (512, hop 128, periodic
+// hann, centred, reflect) -> phase vocoder at rate 2^(-n_steps/12) -> inverse STFT to round(len / rate) samples ->
+// float32-kernel resample int(sr / rate) -> sr -> crop / zero-pad to the input length.
+// The phase vocoder accumulates each bin's phase over ALL frames, including frames where the bin holds nothing but
+// rounding noise; for tonal input the reference's own output therefore depends on FFT rounding at the percent level
+// (measured: two correct float32 STFTs differing by 2e-7 relative change its output by 7e-2 on a unit chirp). Parity
+// is stated accordingly: tight on broadband input, statistical on tonal input (see tests/test_augment_gpu.py).
+constexpr int PS_NFFT = 512, PS_HOP = 128, PS_BINS = 257;
+
+// grid (max frames, B), 256 threads: one frame -> 257 bins by direct DFT (frame-major complex output)
+__global__ void __launch_bounds__(256) pitch_stft_kernel(const float* __restrict__ in, long long in_stride,
+                                                         const AugClip* __restrict__ clips,
+                                                         float* __restrict__ scratch) {
+  const AugClip cl = clips[blockIdx.y];
+  const int f = blockIdx.x;
+  if (cl.kind != SSR_AUG_PITCH || f >= cl.frames) return;
+  __shared__ float xw[PS_NFFT];
+  __shared__ float2 tw[PS_NFFT];
+  const float* x = in + (long long)blockIdx.y * in_stride;
+  for (int n = threadIdx.x; n < PS_NFFT; n += 256) {
+    float s, c;
+    sincospif((float)n * (1.0f / 256.0f), &s, &c);  // angle 2 pi n / 512
+    tw[n] = make_float2(c, s);
+    long long i = (long long)f * PS_HOP + n - PS_NFFT / 2;
+    if (i < 0) i = -i;
+    if (i >= cl.n_in) i = 2LL * (cl.n_in - 1) - i;
+    xw[n] = x[i] * (0.5f - 0.5f * c);  // periodic hann
+  }
+  __syncthreads();
+  float2* spec = reinterpret_cast<float2*>(scratch + cl.spec_off) + (long long)f * PS_BINS;
+  for (int k = threadIdx.x; k < PS_BINS; k += 256) {
+    float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
+    for (int n = 0; n < PS_NFFT; n += 2) {
+      const float2 w0 = tw[(k * n) & (PS_NFFT - 1)];
+      const float2 w1 = tw[(k * (n + 1)) & (PS_NFFT - 1)];
+      re0 = fmaf(xw[n], w0.x, re0);
+      im0 = fmaf(xw[n], w0.y, im0);
+      re1 = fmaf(xw[n + 1], w1.x, re1);
+      im1 = fmaf(xw[n + 1], w1.y, im1);
+    }
+    spec[k] = make_float2(re0 + re1, -(im0 + im1));
+  }
+}
+
+// grid (ceil(257 / 64), B), 64 threads: one thread walks one frequency bin through time (the phase accumulates)
+__global__ void __launch_bounds__(64) pitch_vocoder_kernel(const AugClip* __restrict__ clips,
+                                                           float* __restrict__ scratch) {
+  const AugClip cl = clips[blockIdx.y];
+  const int k = blockIdx.x * 64 + threadIdx.x;
+  if (cl.kind != SSR_AUG_PITCH || k >= PS_BINS) return;
+  const float2* spec = reinterpret_cast<const float2*>(scratch + cl.spec_off);
+  float2* out = reinterpret_cast<float2*>(scratch + cl.spec2_off);
+  // torch.linspace(0, pi * hop, 257) in float32: evaluated from both ends towards the middle
+  const float end = (float)(3.14159265358979323846 * PS_HOP);
+  const float step = __fdiv_rn(end, (float)(PS_BINS - 1));
+  const float pa = k < PS_BINS / 2 ? __fmul_rn(step, (float)k) : __fsub_rn(end, __fmul_rn(step, (float)(PS_BINS - 1 - k)));
+  const float two_pi = 6.28318548202514648f;
+  const float2 first = spec[k];
+  double acc = 0.0;
+  float prev = atan2f(first.y, first.x);  // phase_0
+  for (int i = 0; i < cl.frames2; ++i) {
+    const float ts = (float)(cl.rate * (double)i);
+    const long long i0 = (long long)ts, i1 = (long long)__fadd_rn(ts, 1.0f);
+    const float alpha = fmodf(ts, 1.0f);
+    const float2 s0 = i0 < cl.frames ? spec[i0 * PS_BINS + k] : make_float2(0.f, 0.f);
+    const float2 s1 = i1 < cl.frames ? spec[i1 * PS_BINS + k] : make_float2(0.f, 0.f);
+    const float a0 = atan2f(s0.y, s0.x), a1 = atan2f(s1.y, s1.x);
+    const float n0 = hypotf(s0.x, s0.y), n1 = hypotf(s1.x, s1.y);
+    float ph = __fsub_rn(__fsub_rn(a1, a0), pa);
+    ph = __fsub_rn(ph, __fmul_rn(two_pi, rintf(__fdiv_rn(ph, two_pi))));
+    ph = __fadd_rn(ph, pa);
+    acc += (double)prev;  // cumsum of cat([phase_0, phase[:-1]]), accumulated in double like torch's CPU cumsum
+    prev = ph;
+    const float pacc = (float)acc;
+    const float mag = __fadd_rn(__fmul_rn(alpha, n1), __fmul_rn(__fsub_rn(1.0f, alpha), n0));
+    float s, c;
+    sincosf(pacc, &s, &c);
+    out[(long long)i * PS_BINS + k] = make_float2(mag * c, mag * s);
+  }
+}
+
+// grid (ceil(max n_mid / 128), B), 128 threads: inverse real DFT of the (at most 4) frames covering a sample,
+// windowed overlap-add divided by the window envelope (torch.istft, centred, length = n_mid)
+__global__ void __launch_bounds__(128) pitch_istft_kernel(const AugClip* __restrict__ clips,
+                                                          float* __restrict__ scratch) {
+  const AugClip cl = clips[blockIdx.y];
+  const long long n0 = (long long)blockIdx.x * 128;
+  if (cl.kind != SSR_AUG_PITCH || n0 >= cl.n_mid) return;
+  __shared__ float2 X[4][PS_BINS];
+  __shared__ float2 tw[PS_NFFT];
+  const float2* spec = reinterpret_cast<const float2*>(scratch + cl.spec2_off);
+  float* y = scratch + cl.y_off;
+  const int q = blockIdx.x;
+  for (int n = threadIdx.x; n < PS_NFFT; n += 128) {
+    float s, c;
+    sincospif((float)n * (1.0f / 256.0f), &s, &c);
+    tw[n] = make_float2(c, s);
+  }
+  for (int i = threadIdx.x; i < 4 * PS_BINS; i += 128) {
+    const int fi = i / PS_BINS, k = i - fi * PS_BINS;
+    const int f = q - 1 + fi;
+    X[fi][k] = (f >= 0 && f < cl.frames2) ? spec[(long long)f * PS_BINS + k] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const long long n = n0 + threadIdx.x;
+  if (n >= cl.n_mid) return;
+  const long long pos = n + PS_NFFT / 2;
+  float ysum = 0.f, env = 0.f;
+#pragma unroll 1
+  for (int fi = 0; fi < 4; ++fi) {
+    const int f = q - 1 + fi;
+    if (f < 0 || f >= cl.frames2) continue;
+    const int j = (int)(pos - (long long)f * PS_HOP);  // 0 .. 511 by construction
+    float v0 = X[fi][0].x + ((j & 1) ? -X[fi][PS_BINS - 1].x : X[fi][PS_BINS - 1].x), v1 = 0.f;
+    for (int k = 1; k < PS_BINS - 1; k += 2) {
+      const float2 w0 = tw[(k * j) & (PS_NFFT - 1)];
+      const float2 w1 = tw[((k + 1) * j) & (PS_NFFT - 1)];
+      v0 += 2.0f * (X[fi][k].x * w0.x - X[fi][k].y * w0.y);
+      if (k + 1 < PS_BINS - 1) v1 += 2.0f * (X[fi][k + 1].x * w1.x - X[fi][k + 1].y * w1.y);
+    }
+    const float wj = 0.5f - 0.5f * tw[j].x;
+    ysum = fmaf((v0 + v1) * (1.0f / PS_NFFT), wj, ysum);
+    env = fmaf(wj, wj, env);
+  }
+  y[n] = env > 1e-11f ? ysum / env : 0.f;  // beyond the last frame: zero padding
 }
 
 // ------------------------------------------------------------------------------------------------ counter RNG
@@ -149,6 +315,7 @@ __global__ void __launch_bounds__(256) aug_finish_kernel(const float* __restrict
                                                          const AugClip* __restrict__ clips,
                                                          const float* __restrict__ mid, long long mid_stride,
                                                          const float* __restrict__ noise, long long noise_stride,
+                                                         const float* __restrict__ pscratch,
                                                          float* __restrict__ out, long long out_stride) {
   const AugClip cl = clips[blockIdx.y];
   const float* x = in + (long long)blockIdx.y * in_stride;
@@ -159,6 +326,14 @@ __global__ void __launch_bounds__(256) aug_finish_kernel(const float* __restrict
     const float* m = mid + (long long)blockIdx.y * mid_stride;
     for (long long n = first; n < out_stride; n += step)
       y[n] = n < cl.n_out ? clamp1(resample_one(m, cl.n_mid, cl.n1, cl.o1, n)) : 0.f;
+  } else if (cl.kind == SSR_AUG_PITCH) {
+    // stretched signal -> resample int(sr / rate) -> sr, cropped / zero-padded to the input length
+    const float* m = pscratch + cl.y_off;
+    for (long long n = first; n < out_stride; n += step) {
+      float v = 0.f;
+      if (n < cl.n_out && n < cl.n_res) v = cl.o1 == cl.n1 ? m[n] : resample_one_f32(m, cl.n_mid, cl.o1, cl.n1, n);
+      y[n] = clamp1(v);
+    }
   } else if (cl.kind == SSR_AUG_NOISE && noise != nullptr) {
     // caller-supplied standard-normal noise (the reference's torch.randn_like stream): bit-exact replay of
     // `waveform + noise * noise_factor` (two roundings, no fused multiply-add)
@@ -219,6 +394,78 @@ extern "C" int32_t ssr_augment_out_length(const ssr_aug_op* op, int32_t n, int32
   return ssr_resample_length(ssr_resample_length(n, sample_rate, op->new_rate), op->new_rate, sample_rate);
 }
 
+namespace ssr {
+
+struct AugPlan {
+  std::vector<AugClip> clips;
+  long long max_mid = 0;      // speed: longest intermediate signal
+  long long mid_stride = 0;
+  long long max_frames = 0;   // pitch: most STFT frames / longest stretched signal
+  long long max_stretch = 0;
+  long long pitch_floats = 0; // pitch scratch, in floats
+  bool any_speed = false, any_pitch = false;
+  size_t plan_bytes = 0, mid_bytes = 0, need = 0;
+};
+
+// Host-side plan shared by ssr_augment and ssr_augment_work_bytes. Returns an error text or nullptr.
+static const char* build_plan(const int32_t* n_in, int batch, const ssr_aug_op* ops, int sample_rate,
+                              long long in_stride, AugPlan& P) {
+  P.clips.assign((size_t)batch, AugClip());
+  for (int b = 0; b < batch; ++b) {
+    AugClip& c = P.clips[b];
+    const ssr_aug_op& op = ops[b];
+    memset(&c, 0, sizeof(c));
+    c.kind = op.kind;
+    c.n_in = n_in[b];
+    c.o1 = c.n1 = 1;
+    c.factor = op.factor;
+    c.seed = op.seed;
+    if (c.n_in < 0 || (in_stride >= 0 && c.n_in > in_stride)) return "ssr_augment: n_in out of range";
+    if (op.kind < SSR_AUG_NONE || op.kind > SSR_AUG_PITCH) return "ssr_augment: unknown augmentation kind";
+    if (op.kind == SSR_AUG_SPEED && op.new_rate == sample_rate) c.kind = SSR_AUG_NONE;  // Resample is the identity
+    if (op.kind == SSR_AUG_PITCH && op.new_rate == 0) c.kind = SSR_AUG_NONE;            // n_steps == 0
+    c.n_out = c.n_in;
+    if (c.kind == SSR_AUG_SPEED) {
+      if (op.new_rate <= 0) return "ssr_augment: bad new_rate";
+      const int g = gcd_i(sample_rate, op.new_rate);
+      c.o1 = sample_rate / g;
+      c.n1 = op.new_rate / g;
+      c.n_mid = resampled_len(c.n_in, c.o1, c.n1);
+      c.n_out = resampled_len(c.n_mid, c.n1, c.o1);
+      if (c.n_mid > P.max_mid) P.max_mid = c.n_mid;
+      P.any_speed = true;
+    } else if (c.kind == SSR_AUG_PITCH) {
+      if (op.new_rate < -24 || op.new_rate > 24) return "ssr_augment: pitch n_steps out of range";
+      if (c.n_in <= PS_NFFT / 2) return "ssr_augment: clip too short for the pitch kind (reflect padding needs > 256 samples)";
+      c.rate = pow(2.0, -(double)op.new_rate / 12.0);
+      c.frames = 1 + c.n_in / PS_HOP;
+      c.frames2 = (int)ceil((double)c.frames / c.rate);
+      c.n_mid = (int)nearbyint((double)c.n_in / c.rate);  // python round(): ties to even
+      const int orig = (int)((double)sample_rate / c.rate);
+      const int g = gcd_i(orig, sample_rate);
+      c.o1 = orig / g;
+      c.n1 = sample_rate / g;
+      c.n_res = orig == sample_rate ? c.n_mid : resampled_len(c.n_mid, c.o1, c.n1);
+      c.spec_off = P.pitch_floats;
+      P.pitch_floats += 2LL * c.frames * PS_BINS;
+      c.spec2_off = P.pitch_floats;
+      P.pitch_floats += 2LL * c.frames2 * PS_BINS;
+      c.y_off = P.pitch_floats;
+      P.pitch_floats += ((long long)c.n_mid + 3) & ~3LL;
+      if (c.frames > P.max_frames) P.max_frames = c.frames;
+      if (c.n_mid > P.max_stretch) P.max_stretch = c.n_mid;
+      P.any_pitch = true;
+    }
+  }
+  P.mid_stride = (P.max_mid + 3) & ~3LL;
+  P.plan_bytes = (sizeof(AugClip) * (size_t)batch + 255) & ~(size_t)255;
+  P.mid_bytes = P.any_speed ? ((sizeof(float) * (size_t)P.mid_stride * (size_t)batch + 255) & ~(size_t)255) : 0;
+  P.need = P.plan_bytes + P.mid_bytes + sizeof(float) * (size_t)P.pitch_floats;
+  return nullptr;
+}
+
+}  // namespace ssr
+
 extern "C" int ssr_augment(const float* audio_dev, int64_t in_stride, const int32_t* n_in, int32_t batch,
                            const ssr_aug_op* ops, int32_t sample_rate, const float* noise_dev, int64_t noise_stride,
                            void* work_dev, int64_t work_bytes, float* out_dev, int64_t out_stride, int32_t* n_out,
@@ -229,65 +476,41 @@ extern "C" int ssr_augment(const float* audio_dev, int64_t in_stride, const int3
   cudaStream_t st = (cudaStream_t)cuda_stream;
 
   // host-side plan (pageable: cudaMemcpyAsync stages it before returning, so it may die with this frame)
-  std::vector<AugClip> plan((size_t)batch);
-  long long max_mid = 0;
-  bool any_speed = false;
+  AugPlan P;
+  if (const char* msg = build_plan(n_in, batch, ops, sample_rate, in_stride, P)) return fail(err, err_len, msg);
   for (int b = 0; b < batch; ++b) {
-    AugClip& c = plan[b];
-    const ssr_aug_op& op = ops[b];
-    c.kind = op.kind;
-    c.n_in = n_in[b];
-    c.n_mid = 0;
-    c.o1 = c.n1 = 1;
-    c.factor = op.factor;
-    c.seed = op.seed;
-    if (c.n_in < 0 || c.n_in > in_stride) {
-      return fail(err, err_len, "ssr_augment: n_in out of range");
-    }
-    if (op.kind < SSR_AUG_NONE || op.kind > SSR_AUG_VOLUME) {
-      return fail(err, err_len, "ssr_augment: unknown augmentation kind");
-    }
-    if (op.kind == SSR_AUG_SPEED && op.new_rate == sample_rate) c.kind = SSR_AUG_NONE;  // Resample is the identity
-    if (c.kind == SSR_AUG_SPEED) {
-      if (op.new_rate <= 0) {
-          return fail(err, err_len, "ssr_augment: bad new_rate");
-      }
-      const int g = gcd_i(sample_rate, op.new_rate);
-      c.o1 = sample_rate / g;
-      c.n1 = op.new_rate / g;
-      c.n_mid = resampled_len(c.n_in, c.o1, c.n1);
-      c.n_out = resampled_len(c.n_mid, c.n1, c.o1);
-      if (c.n_mid > max_mid) max_mid = c.n_mid;
-      any_speed = true;
-    } else {
-      c.n_out = c.n_in;
-    }
-    if (c.n_out > out_stride) {
+    if (P.clips[b].n_out > out_stride)
       return fail(err, err_len, "ssr_augment: out_stride too small for the resampled length");
-    }
-    n_out[b] = c.n_out;
+    n_out[b] = P.clips[b].n_out;
   }
-  const long long mid_stride = (max_mid + 3) & ~3LL;
-  const size_t plan_bytes = (sizeof(AugClip) * (size_t)batch + 255) & ~(size_t)255;
-  const size_t need = plan_bytes + (any_speed ? sizeof(float) * (size_t)mid_stride * (size_t)batch : 0);
-  if (!work_dev || (size_t)work_bytes < need) {
+  if (!work_dev || (size_t)work_bytes < P.need) {
     char msg[160];
     snprintf(msg, sizeof msg, "ssr_augment: work buffer too small (%lld bytes given, %zu needed)",
-             (long long)work_bytes, need);
+             (long long)work_bytes, P.need);
     return fail(err, err_len, msg);
   }
   AugClip* plan_dev = reinterpret_cast<AugClip*>(work_dev);
-  float* mid = reinterpret_cast<float*>(reinterpret_cast<char*>(work_dev) + plan_bytes);
-  cudaError_t ce = cudaMemcpyAsync(plan_dev, plan.data(), sizeof(AugClip) * (size_t)batch, cudaMemcpyHostToDevice, st);
-  if (ce == cudaSuccess && any_speed) {
-    dim3 grid((unsigned)((max_mid + 255) / 256), (unsigned)batch);
-    aug_resample_fwd_kernel<<<grid, 256, 0, st>>>(audio_dev, in_stride, plan_dev, mid, mid_stride);
+  float* mid = reinterpret_cast<float*>(reinterpret_cast<char*>(work_dev) + P.plan_bytes);
+  float* pscratch = reinterpret_cast<float*>(reinterpret_cast<char*>(work_dev) + P.plan_bytes + P.mid_bytes);
+  cudaError_t ce =
+      cudaMemcpyAsync(plan_dev, P.clips.data(), sizeof(AugClip) * (size_t)batch, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess && P.any_speed) {
+    dim3 grid((unsigned)((P.max_mid + 255) / 256), (unsigned)batch);
+    aug_resample_fwd_kernel<<<grid, 256, 0, st>>>(audio_dev, in_stride, plan_dev, mid, P.mid_stride);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess && P.any_pitch) {
+    pitch_stft_kernel<<<dim3((unsigned)P.max_frames, (unsigned)batch), 256, 0, st>>>(audio_dev, in_stride, plan_dev,
+                                                                                     pscratch);
+    pitch_vocoder_kernel<<<dim3((PS_BINS + 63) / 64, (unsigned)batch), 64, 0, st>>>(plan_dev, pscratch);
+    pitch_istft_kernel<<<dim3((unsigned)((P.max_stretch + 127) / 128), (unsigned)batch), 128, 0, st>>>(plan_dev,
+                                                                                                      pscratch);
     ce = cudaGetLastError();
   }
   if (ce == cudaSuccess) {
     dim3 grid((unsigned)((out_stride + 255) / 256), (unsigned)batch);
-    aug_finish_kernel<<<grid, 256, 0, st>>>(audio_dev, in_stride, plan_dev, mid, mid_stride, noise_dev, noise_stride,
-                                            out_dev, out_stride);
+    aug_finish_kernel<<<grid, 256, 0, st>>>(audio_dev, in_stride, plan_dev, mid, P.mid_stride, noise_dev,
+                                            noise_stride, pscratch, out_dev, out_stride);
     ce = cudaGetLastError();
   }
   if (ce != cudaSuccess) {
@@ -302,16 +525,7 @@ extern "C" int64_t ssr_augment_work_bytes(const int32_t* n_in, int32_t batch, co
                                           int32_t sample_rate) {
   if (batch <= 0) return 0;
   if (!n_in || !ops || sample_rate <= 0) return -1;
-  long long max_mid = 0;
-  bool any = false;
-  for (int b = 0; b < batch; ++b) {
-    if (ops[b].kind == SSR_AUG_SPEED && ops[b].new_rate != sample_rate && ops[b].new_rate > 0) {
-      const long long m = ssr_resample_length(n_in[b], sample_rate, ops[b].new_rate);
-      if (m > max_mid) max_mid = m;
-      any = true;
-    }
-  }
-  const size_t plan_bytes = (sizeof(AugClip) * (size_t)batch + 255) & ~(size_t)255;
-  const long long mid_stride = (max_mid + 3) & ~3LL;
-  return (int64_t)(plan_bytes + (any ? sizeof(float) * (size_t)mid_stride * (size_t)batch : 0));
+  AugPlan P;
+  if (build_plan(n_in, batch, ops, sample_rate, -1, P) != nullptr) return -1;
+  return (int64_t)P.need;
 }

@@ -154,6 +154,66 @@ def test_properties_at_baseline_batch(aug):
     assert float((z[:, mid] - s[:, mid]).abs().max()) < 2e-3
 
 
+def test_pitch_vs_reference_golden_and_oracle(gold):
+    """The pitch kind (REF/model_training_01.py:174-178) through the drop-in, same seeds as the reference run.
+    Tolerances: tests/test_augment_cpu.py PITCH_TOL (tight on broadband clips, statistical on the tonal chirp)."""
+    import torch
+
+    from oracle import augment_oracle as ao
+    from ssr_b200 import augment, synth
+    from test_augment_cpu import PITCH_TOL, pitch_errors  # tests/ is on sys.path (pytest rootdir-less layout)
+
+    clips = synth.aug_clips()
+    for name in (str(n) for n in gold["pitch_names"]):
+        _, ci, n_steps = name.split("/")
+        ci, n_steps = int(ci), int(n_steps)
+        seed = int(gold[name + "/seed"])
+        random.seed(seed)
+        torch.manual_seed(seed)
+        out = augment.augment_audio(clips[ci].copy(), augmentation_type="pitch", variant="model_training_01")
+        assert out.dtype == np.float32 and out.shape[0] == int(gold[name + "/len"]), name
+        assert not np.array_equal(out, clips[ci]), "augmentation fell back to the input"
+        mx, rel = pitch_errors(out, gold, name)
+        tol_max, tol_rel = PITCH_TOL[ci]
+        assert rel <= tol_rel and (tol_max is None or mx <= tol_max), (name, mx, rel)
+        if ci == 2:  # and against the oracle on the short clip
+            want = ao.apply(clips[ci], "pitch", {"n_steps": n_steps})
+            assert np.abs(out - want).max() <= 1e-3
+
+
+def test_pitch_batch_properties(aug):
+    """Mixed batch with the pitch kind: n_steps = 0 is the identity, short clips are rejected like torch.stft rejects
+    them, the pitch really moves (spectral centroid of a harmonic tone scales by 2^(n/12)), zero padding kept."""
+    import torch
+
+    from ssr_b200.augment import AugOp
+    from ssr_b200.engine import SsrError
+
+    n = 32000
+    t = np.arange(n) / 16000.0
+    tone = (0.3 * np.sin(2 * np.pi * 440.0 * t) + 0.05 * np.random.default_rng(0).standard_normal(n)).astype(np.float32)
+    outs = aug.run([tone, tone, tone, tone[:20000]],
+                   [AugOp("pitch", n_steps=2), AugOp("pitch", n_steps=-2), AugOp("pitch", n_steps=0),
+                    AugOp("volume", factor=0.5)])
+    assert [o.shape[0] for o in outs] == [n, n, n, 20000]
+    np.testing.assert_array_equal(outs[2], tone)
+
+    def peak_hz(x):
+        spec = np.abs(np.fft.rfft(x[4000:-4000] * np.hanning(len(x) - 8000)))
+        return np.argmax(spec) * 16000.0 / (len(x) - 8000)
+
+    assert abs(peak_hz(outs[0]) / 440.0 - 2 ** (2 / 12)) < 0.01
+    assert abs(peak_hz(outs[1]) / 440.0 - 2 ** (-2 / 12)) < 0.01
+    with pytest.raises(SsrError):
+        aug.run([tone[:200]], [AugOp("pitch", n_steps=1)])
+    # the drop-in turns that failure into "return the input" like the reference's except branch
+    from ssr_b200 import augment
+    random.seed(0)  # randint(-2, 2) -> 1
+    short = tone[:200].copy()
+    np.testing.assert_array_equal(augment.augment_audio(short, augmentation_type="pitch", variant="model_training_01"),
+                                  short)
+
+
 def test_augment_and_extract_matches_separate_steps(aug):
     """Batched augment -> encoder on the device equals oracle-augmented clips pushed through the same engine."""
     from oracle import augment_oracle as ao

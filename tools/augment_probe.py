@@ -34,6 +34,7 @@ def main():
         "speed": [AugOp("speed", new_rate=int(16000 * rng.uniform(0.95, 1.05))) for _ in range(B)],
         "noise": [AugOp("noise", factor=0.003, seed=b) for b in range(B)],
         "volume": [AugOp("volume", factor=1.05) for _ in range(B)],
+        "pitch": [AugOp("pitch", n_steps=(-2, -1, 1, 2)[b % 4]) for b in range(B)],
         "mixed": None,
     }
     random.seed(0)
@@ -44,6 +45,20 @@ def main():
         gb = B * n * 4 * 2 * passes / 1e9
         print(f"{name:7s}: {ms:7.3f} ms/batch  {B / ms * 1e3:10.0f} clips/s  {gb / ms * 1e3:7.1f} GB/s algorithmic",
               flush=True)
+    # pitch parity against the committed reference fixture, for the record (same numbers the tests bound)
+    from ssr_b200 import synth
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                "augment.npz"))
+    clips = synth.aug_clips()
+    for name in (str(s) for s in gold["pitch_names"]):
+        _, ci, n_steps = name.split("/")
+        random.seed(int(gold[name + "/seed"]))
+        out = augment.augment_audio(clips[int(ci)].copy(), augmentation_type="pitch", variant="model_training_01")
+        ref = gold[name + "/sub"]
+        d = out[::4].astype(np.float64) - ref
+        print(f"pitch parity {name:12s}: max abs {np.abs(d).max():.2e}  rms err / rms ref "
+              f"{np.sqrt((d ** 2).mean()) / np.sqrt((ref.astype(np.float64) ** 2).mean()):.2e}")
     # CPU reference arithmetic for scale: torchaudio round trip on one clip (co-prime rate)
     import time
 
