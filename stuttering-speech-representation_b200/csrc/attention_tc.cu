@@ -29,6 +29,9 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+// The kernel body holds one code path per template instantiation (bias / no bias); the other one is dead there.
+#pragma nv_diag_suppress 128
+
 namespace ssr {
 
 using namespace ptx;
@@ -249,7 +252,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     const uint32_t quad = warp;  // TMEM lane quadrant accessible to this warp
     const int il = quad * 32 + lane;
     const uint32_t lane_addr = (quad * 32u) << 16;
-    const uint32_t sw = il & 7;
     uint32_t n = 0;
     Item nxt = decode_item(a, blockIdx.x);
     float gate_nxt = 0.f;

@@ -171,7 +171,6 @@ struct WeightMap {
     }
     return it->second->data;
   }
-  bool has(const std::string& name) { return m.count(name) || m.count("encoder." + name); }
 };
 
 template <typename T>

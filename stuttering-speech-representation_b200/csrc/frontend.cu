@@ -8,6 +8,9 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+// wavlm_conv0_kernel<MODE> holds the LayerNorm and the GroupNorm path; one of them is dead per instantiation.
+#pragma nv_diag_suppress 128
+
 namespace ssr {
 
 namespace {
@@ -17,7 +20,6 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------------------------------ waveform statistics
 __global__ void __launch_bounds__(512)
