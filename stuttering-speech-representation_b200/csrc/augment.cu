@@ -42,7 +42,7 @@ struct AugClip {
   double rate;             // 2 ** (-n_steps / 12)
   int frames, frames2;     // STFT frames before / after the phase vocoder
   int n_res;               // length after the final resample (before crop / pad to n_in)
-  long long spec_off, spec2_off, y_off;  // float offsets into the pitch scratch area
+  long long spec_off, spec2_off, fr_off, y_off;  // float offsets into the pitch scratch area
 };
 
 // ------------------------------------------------------------------------------------------------ sinc resampler
@@ -140,39 +140,52 @@ __device__ __forceinline__ float resample_one_f32(const float* __restrict__ x, i
 // is stated accordingly: tight on broadband input, statistical on tonal input (see tests/test_augment_gpu.py).
 constexpr int PS_NFFT = 512, PS_HOP = 128, PS_BINS = 257;
 
-// grid (max frames, B), 256 threads: one frame -> 257 bins by direct DFT (frame-major complex output)
+// In-place radix-2 decimation-in-time FFT of 512 complex points in shared memory by 256 threads (one butterfly each
+// per stage). `s` must hold the input in bit-reversed order; tw[k] = exp(-2 pi i k / 512), k < 256; INVERSE conjugates
+// the twiddles (no 1/N). Ends with a barrier.
+template <bool INVERSE>
+__device__ __forceinline__ void fft512(float2* s, const float2* tw) {
+#pragma unroll 1
+  for (int half = 1; half < PS_NFFT; half <<= 1) {
+    const int pos = threadIdx.x & (half - 1);
+    const int i = ((threadIdx.x - pos) << 1) + pos, j = i + half;
+    float2 w = tw[pos * (PS_NFFT / 2 / half)];
+    if (INVERSE) w.y = -w.y;
+    const float2 a = s[i], b = s[j];
+    const float2 bw = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+    s[i] = make_float2(a.x + bw.x, a.y + bw.y);
+    s[j] = make_float2(a.x - bw.x, a.y - bw.y);
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ int brev9(int n) { return (int)(__brev((unsigned)n) >> 23); }
+
+// grid (max frames, B), 256 threads: one windowed, reflect-padded frame -> 257 bins (frame-major complex output)
 __global__ void __launch_bounds__(256) pitch_stft_kernel(const float* __restrict__ in, long long in_stride,
                                                          const AugClip* __restrict__ clips,
                                                          float* __restrict__ scratch) {
   const AugClip cl = clips[blockIdx.y];
   const int f = blockIdx.x;
   if (cl.kind != SSR_AUG_PITCH || f >= cl.frames) return;
-  __shared__ float xw[PS_NFFT];
-  __shared__ float2 tw[PS_NFFT];
+  __shared__ float2 s[PS_NFFT];
+  __shared__ float2 tw[PS_NFFT / 2];
   const float* x = in + (long long)blockIdx.y * in_stride;
+  {
+    float sn, cs;
+    sincospif((float)threadIdx.x * (1.0f / 256.0f), &sn, &cs);  // angle 2 pi k / 512
+    tw[threadIdx.x] = make_float2(cs, -sn);
+  }
   for (int n = threadIdx.x; n < PS_NFFT; n += 256) {
-    float s, c;
-    sincospif((float)n * (1.0f / 256.0f), &s, &c);  // angle 2 pi n / 512
-    tw[n] = make_float2(c, s);
     long long i = (long long)f * PS_HOP + n - PS_NFFT / 2;
     if (i < 0) i = -i;
     if (i >= cl.n_in) i = 2LL * (cl.n_in - 1) - i;
-    xw[n] = x[i] * (0.5f - 0.5f * c);  // periodic hann
+    const float w = 0.5f - 0.5f * cospif((float)n * (1.0f / 256.0f));  // periodic hann
+    s[brev9(n)] = make_float2(x[i] * w, 0.f);
   }
   __syncthreads();
+  fft512<false>(s, tw);
   float2* spec = reinterpret_cast<float2*>(scratch + cl.spec_off) + (long long)f * PS_BINS;
-  for (int k = threadIdx.x; k < PS_BINS; k += 256) {
-    float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
-    for (int n = 0; n < PS_NFFT; n += 2) {
-      const float2 w0 = tw[(k * n) & (PS_NFFT - 1)];
-      const float2 w1 = tw[(k * (n + 1)) & (PS_NFFT - 1)];
-      re0 = fmaf(xw[n], w0.x, re0);
-      im0 = fmaf(xw[n], w0.y, im0);
-      re1 = fmaf(xw[n + 1], w1.x, re1);
-      im1 = fmaf(xw[n + 1], w1.y, im1);
-    }
-    spec[k] = make_float2(re0 + re1, -(im0 + im1));
-  }
+  for (int k = threadIdx.x; k < PS_BINS; k += 256) spec[k] = s[k];
 }
 
 // grid (ceil(257 / 64), B), 64 threads: one thread walks one frequency bin through time (the phase accumulates)
@@ -212,50 +225,60 @@ __global__ void __launch_bounds__(64) pitch_vocoder_kernel(const AugClip* __rest
   }
 }
 
-// grid (ceil(max n_mid / 128), B), 128 threads: inverse real DFT of the (at most 4) frames covering a sample,
-// windowed overlap-add divided by the window envelope (torch.istft, centred, length = n_mid)
+// grid (ceil(max n_mid / 128), B), 128 threads: overlap-add of the (at most 4) windowed frames covering a sample,
+// divided by the window envelope (torch.istft, centred, length = n_mid); frames come from pitch_iframe_kernel
 __global__ void __launch_bounds__(128) pitch_istft_kernel(const AugClip* __restrict__ clips,
                                                           float* __restrict__ scratch) {
   const AugClip cl = clips[blockIdx.y];
   const long long n0 = (long long)blockIdx.x * 128;
   if (cl.kind != SSR_AUG_PITCH || n0 >= cl.n_mid) return;
-  __shared__ float2 X[4][PS_BINS];
-  __shared__ float2 tw[PS_NFFT];
-  const float2* spec = reinterpret_cast<const float2*>(scratch + cl.spec2_off);
+  const float* fr = scratch + cl.fr_off;
   float* y = scratch + cl.y_off;
   const int q = blockIdx.x;
-  for (int n = threadIdx.x; n < PS_NFFT; n += 128) {
-    float s, c;
-    sincospif((float)n * (1.0f / 256.0f), &s, &c);
-    tw[n] = make_float2(c, s);
-  }
-  for (int i = threadIdx.x; i < 4 * PS_BINS; i += 128) {
-    const int fi = i / PS_BINS, k = i - fi * PS_BINS;
-    const int f = q - 1 + fi;
-    X[fi][k] = (f >= 0 && f < cl.frames2) ? spec[(long long)f * PS_BINS + k] : make_float2(0.f, 0.f);
-  }
-  __syncthreads();
   const long long n = n0 + threadIdx.x;
   if (n >= cl.n_mid) return;
   const long long pos = n + PS_NFFT / 2;
   float ysum = 0.f, env = 0.f;
-#pragma unroll 1
-  for (int fi = 0; fi < 4; ++fi) {
+#pragma unroll
+  for (int fi = 0; fi < 4; ++fi) {  // fixed order: bit-reproducible
     const int f = q - 1 + fi;
     if (f < 0 || f >= cl.frames2) continue;
     const int j = (int)(pos - (long long)f * PS_HOP);  // 0 .. 511 by construction
-    float v0 = X[fi][0].x + ((j & 1) ? -X[fi][PS_BINS - 1].x : X[fi][PS_BINS - 1].x), v1 = 0.f;
-    for (int k = 1; k < PS_BINS - 1; k += 2) {
-      const float2 w0 = tw[(k * j) & (PS_NFFT - 1)];
-      const float2 w1 = tw[((k + 1) * j) & (PS_NFFT - 1)];
-      v0 += 2.0f * (X[fi][k].x * w0.x - X[fi][k].y * w0.y);
-      if (k + 1 < PS_BINS - 1) v1 += 2.0f * (X[fi][k + 1].x * w1.x - X[fi][k + 1].y * w1.y);
-    }
-    const float wj = 0.5f - 0.5f * tw[j].x;
-    ysum = fmaf((v0 + v1) * (1.0f / PS_NFFT), wj, ysum);
+    const float wj = 0.5f - 0.5f * cospif((float)j * (1.0f / 256.0f));
+    ysum += fr[(long long)f * PS_NFFT + j];  // already windowed
     env = fmaf(wj, wj, env);
   }
   y[n] = env > 1e-11f ? ysum / env : 0.f;  // beyond the last frame: zero padding
+}
+
+// grid (max frames2, B), 256 threads: one vocoder frame -> 512 windowed time samples (irfft of the Hermitian
+// extension, 1/N, times the synthesis window)
+__global__ void __launch_bounds__(256) pitch_iframe_kernel(const AugClip* __restrict__ clips,
+                                                           float* __restrict__ scratch) {
+  const AugClip cl = clips[blockIdx.y];
+  const int f = blockIdx.x;
+  if (cl.kind != SSR_AUG_PITCH || f >= cl.frames2) return;
+  __shared__ float2 s[PS_NFFT];
+  __shared__ float2 tw[PS_NFFT / 2];
+  const float2* X = reinterpret_cast<const float2*>(scratch + cl.spec2_off) + (long long)f * PS_BINS;
+  {
+    float sn, cs;
+    sincospif((float)threadIdx.x * (1.0f / 256.0f), &sn, &cs);
+    tw[threadIdx.x] = make_float2(cs, -sn);
+  }
+  for (int k = threadIdx.x; k < PS_BINS; k += 256) {
+    float2 v = X[k];
+    if (k == 0 || k == PS_BINS - 1) v.y = 0.f;  // a real signal's DC / Nyquist bins are real (c2r ignores the rest)
+    s[brev9(k)] = v;
+    if (k > 0 && k < PS_BINS - 1) s[brev9(PS_NFFT - k)] = make_float2(v.x, -v.y);
+  }
+  __syncthreads();
+  fft512<true>(s, tw);
+  float* fr = scratch + cl.fr_off + (long long)f * PS_NFFT;
+  for (int j = threadIdx.x; j < PS_NFFT; j += 256) {
+    const float wj = 0.5f - 0.5f * cospif((float)j * (1.0f / 256.0f));
+    fr[j] = s[j].x * (1.0f / PS_NFFT) * wj;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ counter RNG
@@ -400,7 +423,8 @@ struct AugPlan {
   std::vector<AugClip> clips;
   long long max_mid = 0;      // speed: longest intermediate signal
   long long mid_stride = 0;
-  long long max_frames = 0;   // pitch: most STFT frames / longest stretched signal
+  long long max_frames = 0;   // pitch: most STFT frames (before / after the vocoder) / longest stretched signal
+  long long max_frames2 = 0;
   long long max_stretch = 0;
   long long pitch_floats = 0; // pitch scratch, in floats
   bool any_speed = false, any_pitch = false;
@@ -450,9 +474,12 @@ static const char* build_plan(const int32_t* n_in, int batch, const ssr_aug_op* 
       P.pitch_floats += 2LL * c.frames * PS_BINS;
       c.spec2_off = P.pitch_floats;
       P.pitch_floats += 2LL * c.frames2 * PS_BINS;
+      c.fr_off = P.pitch_floats;
+      P.pitch_floats += (long long)c.frames2 * PS_NFFT;
       c.y_off = P.pitch_floats;
       P.pitch_floats += ((long long)c.n_mid + 3) & ~3LL;
       if (c.frames > P.max_frames) P.max_frames = c.frames;
+      if (c.frames2 > P.max_frames2) P.max_frames2 = c.frames2;
       if (c.n_mid > P.max_stretch) P.max_stretch = c.n_mid;
       P.any_pitch = true;
     }
@@ -503,6 +530,7 @@ extern "C" int ssr_augment(const float* audio_dev, int64_t in_stride, const int3
     pitch_stft_kernel<<<dim3((unsigned)P.max_frames, (unsigned)batch), 256, 0, st>>>(audio_dev, in_stride, plan_dev,
                                                                                      pscratch);
     pitch_vocoder_kernel<<<dim3((PS_BINS + 63) / 64, (unsigned)batch), 64, 0, st>>>(plan_dev, pscratch);
+    pitch_iframe_kernel<<<dim3((unsigned)P.max_frames2, (unsigned)batch), 256, 0, st>>>(plan_dev, pscratch);
     pitch_istft_kernel<<<dim3((unsigned)((P.max_stretch + 127) / 128), (unsigned)batch), 128, 0, st>>>(plan_dev,
                                                                                                       pscratch);
     ce = cudaGetLastError();
