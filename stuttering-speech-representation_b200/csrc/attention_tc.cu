@@ -7,19 +7,18 @@
 //                 all straight out of the fused qkv activation matrix (no head split / transpose pass)
 //     warp 5      single-thread tcgen05.mma issuer. S_{n+1} = Q K^T is issued BEFORE PV_n, so the next block's scores
 //                 are computed while the softmax warps work on the current one:
-//                     S_n  -> TMEM S[n&1] (64 columns) ;  PV_n = P_n V_n -> TMEM O[n&1] (64 columns)
+//                     S_n  -> TMEM S[n&1] (64 columns) ;  O += P_n V_n -> TMEM O (64 columns, one per item)
 //                 (driver warps carry the highest warp ids: the sub-partition arbiter favours them)
 //     warps 0-3   softmax: thread = query row (TMEM lane). tcgen05.ld S, + gated relative-position bias, key mask,
-//                 online max / sum in fp32, P (bf16) -> shared memory P[n&1] in the UMMA 128B-swizzled K-major layout.
-//                 With the gated bias (WavLM, 2-3 blocks per item): PV_{n-1} is folded into an fp32 O accumulator in
-//                 registers one block LATE, i.e. after P_n has been handed to the tensor core, by which time it has
-//                 long completed; no TMEM read-modify-write is needed for the online-softmax rescale.
-//                 Without bias (Whisper, 24 blocks per item): O accumulates in TMEM over the whole item against the
-//                 block-0 reference maximum; no per-element maximum is tracked afterwards. A stale reference only
-//                 shifts the exponent (bf16 and fp32 share its range); if a block's partial sum leaves the safe range
-//                 the warp rescales its rows of O in TMEM in place and redoes the block (rare). Measured on B200 at
-//                 B=64, T=1500, H=20: 1.91 ms -> 1.31 ms per layer for peaked scores (no redo any more), 1.50 ms for
-//                 flat scores (denser P: the kernel is power-limited, 1.78 of 1.965 GHz under ncu).
+//                 fp32 sum, P (bf16) -> shared memory P[n&1] in the UMMA 128B-swizzled K-major layout.
+//                 O accumulates in TMEM over the whole item against the block-0 reference maximum (exact row maximum
+//                 of the first block); no per-element maximum is tracked afterwards. A stale reference only shifts
+//                 the exponent (bf16 and fp32 share its range); if a block's partial sum leaves the safe range the
+//                 warp rescales its rows of O in TMEM in place and redoes the block (rare). The softmax warps wait for
+//                 a tensor-core round trip once per item (PV of the last block). Measured on B200: Whisper shape
+//                 (B=64, T=1500, H=20) 1.91 ms -> 1.29 ms per layer on peaked scores, 1.50 ms on flat scores (denser
+//                 P: the kernel is power-limited, 1.78 of 1.965 GHz under ncu); WavLM shape (B=256, T=149, H=16, gated
+//                 bias) 183 -> 168 us versus a per-block two-pass online softmax with a register accumulator.
 //   Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each). Padding is not computed: the last key
 //   block uses an MMA N / K extent rounded to 16 live keys, softmax touches only the 32-column chunks that hold live
 //   keys, and warps whose 32 query rows are all beyond the clip's length only keep the barrier protocol going.
@@ -28,9 +27,6 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
-
-// The kernel body holds one code path per template instantiation (bias / no bias); the other one is dead there.
-#pragma nv_diag_suppress 128
 
 namespace ssr {
 
@@ -51,7 +47,7 @@ constexpr int SM_P = SM_KV + KV_STAGES * 2 * KV_BYTES;       // 2 buffers
 constexpr int SM_BAR = SM_P + 2 * P_BYTES;
 constexpr int ATT_SMEM = SM_BAR + 256;
 constexpr int TMEM_COLS = 256;
-constexpr int TM_S = 0, TM_O = 128;  // S[2] at columns 0 / 64, O[2] at columns 128 / 192
+constexpr int TM_S = 0, TM_O = 128;  // S[2] at columns 0 / 64, O at columns 128..191 (allocation is a power of two)
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -92,14 +88,15 @@ __device__ __forceinline__ Item decode_item(const AttentionArgs& a, int idx) {
   return it;
 }
 
-constexpr float LAZY_T = 8.0f;
 
 // One 32-key chunk of one query row: scores (+ gated relative-position bias, + key mask) -> running block max and,
 // if WRITE_P, probabilities exp(s - ref) accumulated into l_blk and stored as bf16 into the row's P tile columns
 // col0 .. col0+3 (16-byte units, XOR-swizzled by row % 8 = the UMMA / TMA 128B swizzle).
-template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX = true>
-__device__ __forceinline__ void chunk(const uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel,
-                                      float mu2, float& m_blk, float& l_blk, uint8_t* prow, uint32_t col0) {
+// WRITE_BACK keeps the biased / masked scores in `raw`, so that a second pass over the same registers needs neither
+// the bias table nor the mask again.
+template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX = true, bool WRITE_BACK = false>
+__device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel, float mu2,
+                                      float& m_blk, float& l_blk, uint8_t* prow, uint32_t col0) {
   uint32_t packed[16];
 #pragma unroll
   for (int k = 0; k < 32; k += 2) {
@@ -111,6 +108,10 @@ __device__ __forceinline__ void chunk(const uint32_t (&raw)[32], int jg0, int le
     if (MASK) {
       if (jg0 + k >= len) v0 = -INFINITY;
       if (jg0 + k + 1 >= len) v1 = -INFINITY;
+    }
+    if (WRITE_BACK) {
+      raw[k] = __float_as_uint(v0);
+      raw[k + 1] = __float_as_uint(v1);
     }
     if (TRACK_MAX) m_blk = fmaxf(m_blk, fmaxf(v0, v1));
     if (WRITE_P) {
@@ -201,10 +202,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     uint32_t n_item = 0, n = 0;
     bool have_prev = false, prev_first = false;
     int prev_n16 = 0;
-    // PV of block n-1 is issued after S of block n.
-    // HAS_BIAS: PV_n -> O[n&1], fresh per block (the softmax warps fold it into registers).
-    // else:     PV_n accumulates into the single O[0] over the whole item (rescaled in place on the rare occasion the
-    //           softmax reference changes).
+    // PV of block n-1 is issued after S of block n and accumulates into O over the whole item (the softmax warps
+    // rescale O in place on the rare occasion the softmax reference changes).
     auto issue_pv_prev = [&]() {
       const uint32_t pn = n - 1;
       const int ps = pn % KV_STAGES;
@@ -212,8 +211,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       tc_fence_after();
       const uint64_t dp = umma_desc_sw128(smem_u32(smem + SM_P + (pn & 1) * P_BYTES));
       const uint64_t dv = umma_desc_sw128_mn(smem_u32(smem + SM_KV + ps * 2 * KV_BYTES + KV_BYTES));
-      const uint32_t d_o = tmem + TM_O + (HAS_BIAS ? (pn & 1) * 64 : 0);
-      const bool keep = !HAS_BIAS && !prev_first;
+      const uint32_t d_o = tmem + TM_O;
+      const bool keep = !prev_first;
       for (int k = 0; k < prev_n16; ++k)  // 16 keys per MMA: P advances 32 B, V two 8-row groups = 2048 B
         umma_bf16(d_o, dp + 2 * k, dv + (uint64_t)(k * 2048 >> 4), idesc_pv, (keep || k != 0) ? 1u : 0u);
       umma_commit(&kv_empty[ps]);
@@ -272,8 +271,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       const bool warp_live = it.q0 + (int)quad * 32 < it.len;   // at least one live query row in this warp
       const float* rel = nullptr;
       if (HAS_BIAS) rel = a.relbias + (long long)it.h * a.rel_stride + a.rel_center - i;  // rel[j] = table[h][j - i]
-      if constexpr (!HAS_BIAS) {
-        // ---------------- long sequences without bias (Whisper): O accumulates in TMEM over the whole item ----------
+      {
+        // ---------------- O accumulates in TMEM over the whole item ----------
         // Block 0 takes the exact row maximum as the softmax reference. Later blocks exponentiate against that
         // (possibly stale) reference without tracking a maximum at all: any shift of the reference is mathematically
         // exact, and bf16 / fp32 share the exponent range, so a probability far above 1 is harmless. Only if a block's
@@ -297,35 +296,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             tmem_ld_32x32(ts, r0);
             if (nch == 2) tmem_ld_32x32(ts + 32, r1);
             tmem_wait_ld();
+            float mu2;
             if (j == 0) {
+              // exact row maximum of the first block; the biased / masked scores stay in the registers
               float m_blk = -INFINITY;
               if (nch == 2) {
-                chunk<false, false, false>(r0, k0, it.len, 0.f, nullptr, 0.f, m_blk, l_blk, nullptr, 0);
-                chunk<false, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, false, false, true, HAS_BIAS>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, true, false, true, true>(r1, k0 + 32, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
               } else {
-                chunk<false, true, false>(r0, k0, it.len, 0.f, nullptr, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, true, false, true, true>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
               }
               m_ref = m_blk;
-            }
-            float mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-            if (nch == 2) {
+              mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
               chunk<false, false, true, false>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
-              if (need_mask)
-                chunk<false, true, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
-              else
-                chunk<false, false, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
+              if (nch == 2) chunk<false, false, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
             } else {
-              if (need_mask)
-                chunk<false, true, true, false>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
-              else
-                chunk<false, false, true, false>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
+              mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
+              if (nch == 2) {
+                chunk<HAS_BIAS, false, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+                if (need_mask)
+                  chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel, mu2, dummy, l_blk, prow, 4);
+                else
+                  chunk<HAS_BIAS, false, true, false>(r1, k0 + 32, it.len, gate, rel, mu2, dummy, l_blk, prow, 4);
+              } else {
+                if (need_mask)
+                  chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+                else
+                  chunk<HAS_BIAS, false, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+              }
             }
             const bool unsafe = !(l_blk < L_SAFE);  // also true for NaN / inf
             if (j > 0 && __any_sync(0xffffffffu, unsafe)) {
               // rare: raise the reference to this block's exact maximum (rows that do not need it keep theirs)
               float m_blk = -INFINITY, l_dummy = 0.f;
-              chunk<false, true, false>(r0, k0, it.len, 0.f, nullptr, 0.f, m_blk, l_dummy, nullptr, 0);
-              if (nch == 2) chunk<false, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, 0.f, m_blk, l_dummy, nullptr, 0);
+              chunk<HAS_BIAS, true, false>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_dummy, nullptr, 0);
+              if (nch == 2) chunk<HAS_BIAS, true, false>(r1, k0 + 32, it.len, gate, rel, 0.f, m_blk, l_dummy, nullptr, 0);
               const float m_new = unsafe ? fmaxf(m_ref, m_blk) : m_ref;
               const float alpha = (m_new == m_ref) ? 1.f : ex2_approx((m_ref - m_new) * LOG2E);
               m_ref = m_new;
@@ -350,8 +355,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 tmem_wait_st();
               }
               l_blk = 0.f;
-              chunk<false, true, true, false>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
-              if (nch == 2) chunk<false, true, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
+              chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+              if (nch == 2) chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel, mu2, dummy, l_blk, prow, 4);
             }
             l_run += l_blk;
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -388,159 +393,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           }
         }
         tc_fence_before();  // the TMEM reads above are ordered before the bar_p arrival that lets the next item's PV overwrite O
-        continue;
-      }
-      float o[64];
-#pragma unroll
-      for (int d = 0; d < 64; ++d) o[d] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f;
-      float alpha_pend = 1.f;  // rescale that goes with the not-yet-folded PV of the previous block
-
-      // fold PV of block `pn` (already relative to the running max at that block) into the accumulator
-      auto fold = [&](uint32_t pn, float alpha) {
-        mbar_wait(&bar_o[pn & 1], (pn >> 1) & 1);
-        __syncwarp();
-        tc_fence_after();
-        if (warp_live) {
-          uint32_t r0[32], r1[32];  // both halves in flight before the single wait
-          tmem_ld_32x32(tmem + lane_addr + TM_O + (pn & 1) * 64, r0);
-          tmem_ld_32x32(tmem + lane_addr + TM_O + (pn & 1) * 64 + 32, r1);
-          tmem_wait_ld();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] = fmaf(o[k], alpha, __uint_as_float(r0[k]));
-#pragma unroll
-          for (int k = 0; k < 32; ++k) o[32 + k] = fmaf(o[32 + k], alpha, __uint_as_float(r1[k]));
-        }
-        tc_fence_before();
-      };
-
-      for (int j = 0; j < it.nkb; ++j, ++n) {
-        const int k0 = j * KBLK;
-        const int nlive = min(KBLK, it.len - k0);
-        const int nch = (nlive + 31) >> 5;  // 32-column chunks that hold live keys (1 or 2)
-        const bool need_mask = (nlive & 31) != 0;
-        const uint32_t ts = tmem + lane_addr + TM_S + (n & 1) * 64;
-        uint8_t* prow = smem + SM_P + (n & 1) * P_BYTES + il * 128;
-        mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
-        __syncwarp();
-        tc_fence_after();
-        float alpha = 1.f;
-        if (warp_live && HAS_BIAS) {
-          // Short sequences with the gated bias (WavLM): classic two-pass online softmax per block (measured faster
-          // than the lazy variant for 2-3 blocks per item).
-          // Pass 1 adds the bias / mask, takes the row maximum and writes the biased scores back to TMEM, so pass 2
-          // does not touch the bias table again.
-          float m_blk = -INFINITY, l_blk = 0.f;
-          for (int c = 0; c < nch; ++c) {
-            uint32_t raw[32];
-            tmem_ld_32x32(ts + c * 32, raw);
-            tmem_wait_ld();
-            const int jg0 = k0 + c * 32;
-            const bool mask_here = need_mask && c == nch - 1;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              float v = fmaf(gate, __ldg(rel + jg0 + k), __uint_as_float(raw[k]));
-              if (mask_here && jg0 + k >= it.len) v = -INFINITY;
-              m_blk = fmaxf(m_blk, v);
-              raw[k] = __float_as_uint(v);
-            }
-            tmem_st_32x32(ts + c * 32, raw);
-          }
-          tmem_wait_st();
-          const float m_new = fmaxf(m_run, m_blk);
-          const float mu = (m_new == -INFINITY) ? 0.f : m_new;
-          alpha = ex2_approx((m_run - mu) * LOG2E);
-          const float mu2 = mu * LOG2E;
-          m_run = m_new;
-          float dummy = -INFINITY;
-          for (int c = 0; c < nch; ++c) {
-            uint32_t raw[32];
-            tmem_ld_32x32(ts + c * 32, raw);
-            tmem_wait_ld();
-            chunk<false, false, true>(raw, k0 + c * 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, c * 4);
-          }
-          l_run = l_run * alpha + l_blk;
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        } else if (warp_live) {
-          float m_blk = -INFINITY, l_blk = 0.f;
-          if (j == 0) {
-            // first block of the item: exact row maximum first (nothing to rescale yet)
-            for (int c = 0; c < nch; ++c) {
-              uint32_t raw[32];
-              tmem_ld_32x32(ts + c * 32, raw);
-              tmem_wait_ld();
-              if (need_mask && c == nch - 1)
-                chunk<HAS_BIAS, true, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
-              else
-                chunk<HAS_BIAS, false, false>(raw, k0 + c * 32, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
-            }
-            m_run = m_blk;
-          }
-          // probabilities relative to the running reference max m_run (possibly stale: see below)
-          float mu2 = ((m_run == -INFINITY) ? 0.f : m_run) * LOG2E;
-          if (nch == 2) {
-            uint32_t r0[32], r1[32];  // both chunks in flight before the single wait
-            tmem_ld_32x32(ts, r0);
-            tmem_ld_32x32(ts + 32, r1);
-            tmem_wait_ld();
-            chunk<HAS_BIAS, false, true>(r0, k0, it.len, gate, rel, mu2, m_blk, l_blk, prow, 0);
-            if (need_mask)
-              chunk<HAS_BIAS, true, true>(r1, k0 + 32, it.len, gate, rel, mu2, m_blk, l_blk, prow, 4);
-            else
-              chunk<HAS_BIAS, false, true>(r1, k0 + 32, it.len, gate, rel, mu2, m_blk, l_blk, prow, 4);
-          } else {
-            uint32_t raw[32];
-            tmem_ld_32x32(ts, raw);
-            tmem_wait_ld();
-            if (need_mask)
-              chunk<HAS_BIAS, true, true>(raw, k0, it.len, gate, rel, mu2, m_blk, l_blk, prow, 0);
-            else
-              chunk<HAS_BIAS, false, true>(raw, k0, it.len, gate, rel, mu2, m_blk, l_blk, prow, 0);
-          }
-          // Lazy online softmax: later blocks keep the reference max unless the block maximum exceeds it by more
-          // than LAZY_T (probabilities then stay below e^LAZY_T, harmless in bf16 / fp32); only then is the block
-          // redone against the new maximum and the accumulated state rescaled. Any shift is mathematically exact.
-          const bool redo = (j > 0) && (m_blk > m_run + LAZY_T);
-          if (__any_sync(0xffffffffu, redo)) {
-            if (redo) {
-              alpha = ex2_approx((m_run - m_blk) * LOG2E);
-              m_run = m_blk;
-            }
-            mu2 = ((m_run == -INFINITY) ? 0.f : m_run) * LOG2E;
-            l_blk = 0.f;
-            float dummy = -INFINITY;
-            for (int c = 0; c < nch; ++c) {
-              uint32_t raw[32];
-              tmem_ld_32x32(ts + c * 32, raw);
-              tmem_wait_ld();
-              chunk<HAS_BIAS, true, true>(raw, k0 + c * 32, it.len, gate, rel, mu2, dummy, l_blk, prow, c * 4);
-            }
-          }
-          l_run = l_run * alpha + l_blk;
-          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[n & 1]);
-        // ---- late fold: PV of the previous block of this item completed while this block's softmax ran ----
-        if (j > 0) fold(n - 1, alpha_pend);
-        alpha_pend = alpha;
-      }
-      fold(n - 1, alpha_pend);  // last block of the item: the one true round-trip wait per item
-      // ---- normalise and store this row (rows at or beyond the clip length are never read downstream) ----
-      if (i < it.len) {
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-        uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)row0 + i) * a.D + it.h * HD);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 pk = __floats2bfloat162_rn(o[q * 8 + 2 * e] * inv, o[q * 8 + 2 * e + 1] * inv);
-            w[e] = *reinterpret_cast<uint32_t*>(&pk);
-          }
-          dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
-        }
       }
     }
   }
