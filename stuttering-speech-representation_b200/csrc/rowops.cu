@@ -99,6 +99,9 @@ layernorm_kernel(const LayerNormArgs a) {
     const int sub = lane & 15;
     const float4 wa = __ldg(reinterpret_cast<const float4*>(a.gate_wa) + sub);
     const float4 wb = __ldg(reinterpret_cast<const float4*>(a.gate_wb) + sub);
+    // The 16-lane sums of slot i are kept by lane `sub == i`, so that the sigmoids of all 2 * NV heads are evaluated
+    // once, in parallel, instead of by two live lanes per slot.
+    float my_da = 0.f, my_db = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float da = v[i][0] * wa.x + v[i][1] * wa.y + v[i][2] * wa.z + v[i][3] * wa.w;
@@ -108,12 +111,16 @@ layernorm_kernel(const LayerNormArgs a) {
         da += __shfl_xor_sync(0xffffffffu, da, o);
         db += __shfl_xor_sync(0xffffffffu, db, o);
       }
-      if (sub == 0) {
-        const int h = i * 2 + (lane >> 4);
-        const float ga = 1.0f / (1.0f + expf(-(da + a.gate_ba)));
-        const float gb = 1.0f / (1.0f + expf(-(db + a.gate_bb)));
-        a.gate_out[row * a.n_heads + h] = ga * (gb * __ldg(a.gate_const + h) - 1.0f) + 2.0f;
+      if (sub == i) {
+        my_da = da;
+        my_db = db;
       }
+    }
+    if (sub < NV) {
+      const int h = sub * 2 + (lane >> 4);
+      const float ga = 1.0f / (1.0f + expf(-(my_da + a.gate_ba)));
+      const float gb = 1.0f / (1.0f + expf(-(my_db + a.gate_bb)));
+      a.gate_out[row * a.n_heads + h] = ga * (gb * __ldg(a.gate_const + h) - 1.0f) + 2.0f;
     }
   }
 }
