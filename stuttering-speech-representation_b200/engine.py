@@ -155,6 +155,62 @@ class _EngineBase:
             raise SsrError(self._err())
         return out_host
 
+    def pooled_stream(self, batches, depth: int = 2):
+        """Throughput path over many batches. `batches` yields (audio_host [B, ld] float32 — pinned for full PCIe
+        speed —, n_samples [B]); this generator yields one pinned float32 [B, L+1, D] tensor per batch, in order.
+        The H2D copy of batch i+1 and the D2H copy of batch i-1 overlap the forward of batch i (three CUDA streams,
+        `depth` buffers each), so the copies the synchronous `pooled_pinned` pays per call disappear from the
+        critical path. A yielded tensor is a view of a reused pinned buffer: consume (or copy) it before advancing
+        the generator again. With a problem in one batch the SsrError surfaces from the generator."""
+        dev = torch.device("cuda", self.device)
+        L1, D = self.layers + 1, self.hidden
+        # streams and (pinned / device) buffers live on the engine: allocating pinned memory per call would cost more
+        # than the copies this path hides
+        st = getattr(self, "_stream_state", None)
+        if st is None or len(st["dev_in"]) != depth:
+            st = {"streams": tuple(torch.cuda.Stream(dev) for _ in range(3)), "dev_in": [None] * depth,
+                  "dev_out": [None] * depth, "pin_out": [None] * depth}
+            self._stream_state = st
+        s_in, s_run, s_out = st["streams"]
+        dev_in, dev_out, pin_out = st["dev_in"], st["dev_out"], st["pin_out"]
+        torch.cuda.synchronize(dev)  # a previous, abandoned generator may have left work on the side streams
+        run_done = [torch.cuda.Event() for _ in range(depth)]
+        in_ready = [torch.cuda.Event() for _ in range(depth)]
+        out_done = [torch.cuda.Event() for _ in range(depth)]
+        pending = []
+        for k, (ah, n) in enumerate(batches):
+            slot = k % depth
+            ah = torch.as_tensor(ah)
+            assert not ah.is_cuda and ah.dtype == torch.float32 and ah.dim() == 2 and ah.stride(1) == 1
+            B, ld = ah.shape
+            if dev_in[slot] is None or dev_in[slot].shape[0] < B or dev_in[slot].shape[1] != ld:
+                torch.cuda.synchronize(dev)  # (re)allocation: nothing may still be using the old buffer
+                dev_in[slot] = torch.empty((B, ld), dtype=torch.float32, device=dev)
+            if dev_out[slot] is None or dev_out[slot].shape[0] < B:
+                torch.cuda.synchronize(dev)
+                dev_out[slot] = torch.empty((B, L1, D), dtype=torch.float32, device=dev)
+                pin_out[slot] = torch.empty((B, L1, D), dtype=torch.float32).pin_memory()
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(run_done[slot])      # the forward that last read this input buffer has finished
+                dev_in[slot][:B].copy_(ah, non_blocking=True)
+                in_ready[slot].record(s_in)
+            s_run.wait_event(in_ready[slot])
+            s_run.wait_event(out_done[slot])         # the D2H that last read this output buffer has finished
+            self.pooled_device(dev_in[slot][:B], n, out=dev_out[slot][:B], stream=s_run)
+            run_done[slot].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(run_done[slot])
+                pin_out[slot][:B].copy_(dev_out[slot][:B], non_blocking=True)
+                out_done[slot].record(s_out)
+            pending.append((slot, B))
+            if len(pending) == depth:
+                s0, b0 = pending.pop(0)
+                out_done[s0].synchronize()
+                yield pin_out[s0][:b0]
+        for s0, b0 in pending:
+            out_done[s0].synchronize()
+            yield pin_out[s0][:b0]
+
     def pooled(self, clips: Sequence) -> np.ndarray:
         """Host in, host out (the call the drop-in shim makes): list of 1-D float clips -> float32 [B, L+1, D]."""
         if len(clips) == 0:

@@ -334,6 +334,30 @@ def test_batch_shims_match_per_clip_shims():
             np.testing.assert_allclose(one[k], d[k], rtol=0, atol=2e-6 * max(1.0, np.abs(d[k]).max()))
 
 
+def test_pooled_stream_matches_synchronous_calls():
+    """The streaming API (copies overlapped with neighbouring batches on side streams) returns, in order, exactly what
+    the synchronous host call returns — including a shorter last batch and a change of clip length."""
+    import torch
+
+    from ssr_b200 import synth
+
+    _, _, eng = wavlm("tiny_stable")
+    batches = []
+    for k, (B, n) in enumerate([(5, 16000), (5, 16000), (5, 16000), (3, 16000), (4, 24000), (4, 24000)]):
+        x = np.stack([synth.clip_by_index(100 * k + i, n) for i in range(B)])
+        batches.append((torch.from_numpy(x).pin_memory(), np.full(B, n, np.int32)))
+    want = []
+    for x, n in batches:
+        out = torch.empty((x.shape[0], eng.layers + 1, eng.hidden)).pin_memory()
+        want.append(eng.pooled_pinned(x, n, out).numpy().copy())
+    got = [t.numpy().copy() for t in eng.pooled_stream(iter(batches))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape
+        np.testing.assert_array_equal(g, w)
+    assert list(eng.pooled_stream(iter([]))) == []
+
+
 def test_pipeline_split_extraction_with_engine(tmp_path):
     """SURVEY 8(f)-2 end to end: batched engine -> the reference's on-disk layout -> read back."""
     from ssr_b200 import pipeline, synth

@@ -15,6 +15,10 @@ SHAPES = {  # name: (M, N, K, bias, act, resid, f32_out, bf16_out)
     "ffn1": (38400, 4096, 1024, 1, 1, 0, 0, 1),
     "ffn2": (38400, 1024, 4096, 1, 0, 1, 1, 0),
     "plain": (38400, 4096, 1024, 0, 0, 0, 0, 1),
+    # out-proj variants: which part of the epilogue traffic costs what
+    "out_f32_noresid": (38400, 1024, 1024, 1, 0, 0, 1, 0),
+    "out_bf16_noresid": (38400, 1024, 1024, 1, 0, 0, 0, 1),
+    "out_bf16_resid": (38400, 1024, 1024, 1, 0, 1, 0, 1),
 }
 
 
