@@ -334,6 +334,39 @@ def test_batch_shims_match_per_clip_shims():
             np.testing.assert_allclose(one[k], d[k], rtol=0, atol=2e-6 * max(1.0, np.abs(d[k]).max()))
 
 
+def test_engine_lifecycle_releases_device_memory():
+    """ssr_create / run / ssr_destroy in a loop: the arena, packed weights and staging buffers all go back."""
+    import gc
+
+    import torch
+
+    from ssr_b200 import WavLMEngine, synth
+
+    model, fe = synth.build_wavlm("tiny_stable")
+    clips = synth.mixed_clips()[:3]
+
+    def cycle():
+        eng = WavLMEngine.from_hf(model, fe)
+        out = eng.pooled(clips)
+        eng.close()
+        return out
+
+    ref = cycle()
+    gc.collect()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(6):
+        np.testing.assert_array_equal(cycle(), ref)
+    gc.collect()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, f"leaked {(free0 - free1) >> 20} MiB over 6 create/destroy cycles"
+    with pytest.raises(Exception):
+        eng = WavLMEngine.from_hf(model, fe)
+        eng.close()
+        eng.pooled(clips)  # a closed engine must fail loudly, not crash
+
+
 def test_pooled_stream_matches_synchronous_calls():
     """The streaming API (copies overlapped with neighbouring batches on side streams) returns, in order, exactly what
     the synchronous host call returns — including a shorter last batch and a change of clip length."""
