@@ -125,6 +125,44 @@ def test_wavlm_vs_oracle_and_variants(name):
     check_pooled(mma, base, f"{name} tcgen05 vs mma.sync attention", cos_min=0.99999, rel_max=8e-3)
 
 
+def test_trained_like_statistics_vs_oracle():
+    """Random-init weights give flat attention and tame activations; trained checkpoints do not. Scale the q / k
+    projections (peaked attention: exercises the stale-reference softmax in a full model), the FFN (larger residual
+    stream) and plant outlier channels in the LayerNorm gains, then hold the same tolerance against the oracle."""
+    import torch
+
+    from oracle.wavlm_oracle import WavLMOracle
+    from oracle.whisper_oracle import WhisperEncoderOracle
+    from ssr_b200 import WavLMEngine, WhisperEncoderEngine, synth
+    from ssr_b200.melfilters import whisper_mel_filters
+
+    def sharpen(model, qk, ffn):
+        with torch.no_grad():
+            for name, p in model.named_parameters():
+                if name.endswith(("q_proj.weight", "k_proj.weight")):
+                    p.mul_(qk)
+                elif name.endswith(("intermediate_dense.weight", "fc1.weight")):
+                    p.mul_(ffn)
+                elif name.endswith("layer_norm.weight") and p.numel() >= 256:
+                    p[::97].mul_(6.0)  # a few outlier channels
+
+    clips = synth.mixed_clips()[:3]
+    model, fe = synth.build_wavlm("tiny_stable", seed=3)
+    sharpen(model, 5.0, 2.0)
+    eng = WavLMEngine.from_hf(model, fe)
+    orc = WavLMOracle.from_hf(model)
+    ref = np.stack([orc.pooled(c, fe.do_normalize) for c in clips])
+    check_pooled(eng.pooled(clips), ref, "wavlm tiny_stable, sharpened")
+
+    enc, wfe = synth.build_whisper_encoder("tiny", seed=3)
+    sharpen(enc, 6.0, 2.0)
+    weng = WhisperEncoderEngine.from_hf(enc, wfe)
+    worc = WhisperEncoderOracle.from_hf(enc)
+    mf = whisper_mel_filters(80)
+    wref = np.stack([worc.pooled(c, mf) for c in clips[:2]])
+    check_pooled(weng.pooled(clips[:2]), wref, "whisper tiny, sharpened")
+
+
 def test_wavlm_large_posconv_variants():
     from ssr_b200 import synth
 
