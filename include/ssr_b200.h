@@ -64,7 +64,9 @@ void ssr_destroy(ssr_engine* e);
 const char* ssr_last_error(const ssr_engine* e);
 
 /* Options: "simt_gemm" (bring-up cross-check GEMM), "fused_pool" (default 1), "snapshot_layer" (-1 = off),
- * "attn_simt" (1 = mma.sync attention cross-check kernel),
+ * "attn_simt" (1 = mma.sync attention cross-check kernel), "posconv_generic" (1 = positional conv through the generic
+ * GEMM), "graphs" (default 1: the *_host entry points replay a captured CUDA graph when a small batch (B <= 16)
+ * repeats the previous call's batch size, pitch and lengths — the reference's per-clip loop over equal-length clips),
  * "profile" (1 = bracket every kernel launch with CUDA events on the launching stream; read with ssr_profile_fetch).
  * Returns 0, or -1 for an unknown key. */
 int ssr_set_option(ssr_engine* e, const char* key, int32_t value);

@@ -31,7 +31,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import SsrError, _as_f32_clip
+from .engine import SsrError, _as_f32_clip, row_pitch
 
 logger = logging.getLogger("ssr_b200")
 
@@ -122,10 +122,10 @@ class Augmenter:
         n_out = np.zeros(B, dtype=np.int32)
         err = C.create_string_buffer(256)
         st = torch.cuda.current_stream(audio.device) if stream is None else stream
-        rc = self._lib.ssr_augment(audio.data_ptr(), audio.stride(0), n_in_p, B, c_ops, self.sample_rate,
+        rc = self._lib.ssr_augment(audio.data_ptr(), row_pitch(audio), n_in_p, B, c_ops, self.sample_rate,
                                    None if noise is None else noise.data_ptr(),
-                                   0 if noise is None else noise.stride(0), self._work.data_ptr(),
-                                   self._work.numel(), out.data_ptr(), out.stride(0),
+                                   0 if noise is None else row_pitch(noise), self._work.data_ptr(),
+                                   self._work.numel(), out.data_ptr(), row_pitch(out),
                                    n_out.ctypes.data_as(_lib.c_i32p), st.cuda_stream, err, 256)
         if rc != 0:
             raise SsrError(err.value.decode(errors="replace"))

@@ -42,6 +42,10 @@ inline uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 
+// Bumped by every workspace (re)allocation: cached device state that bakes pointers in (uploaded lengths, captured
+// CUDA graphs) is only valid for the epoch it was made in.
+uint64_t g_arena_epoch = 1;
+
 struct Buf {
   void* p = nullptr;
   size_t cap = 0;
@@ -51,6 +55,7 @@ struct Buf {
   // Grow-only; new memory is zero-filled (padding regions rely on it and are never written afterwards).
   int ensure(size_t bytes, cudaStream_t st, std::string& err) {
     if (bytes <= cap) return 0;
+    ++g_arena_epoch;
     if (p) {
       CK(cudaStreamSynchronize(st));
       CK(cudaFree(p));
@@ -145,7 +150,38 @@ struct ssr_engine {
   Buf snap[8];
   std::map<std::string, DbgBuf> dbg;
 
+  // ---- host-entry plumbing ----
+  // what nsamp_dev / lens_dev currently hold (skips two pageable H2D copies when a call repeats the lengths)
+  std::vector<int> up_nsamp, up_lens;
+  const void *up_ptr_n = nullptr, *up_ptr_l = nullptr;
+  cudaStream_t up_stream = nullptr;
+  bool capturing = false;
+  // Small host-entry batches are launch-latency bound (about 210 kernels per WavLM-Large forward): the second
+  // identical call (same model path, batch, pitch and lengths — the reference's per-clip loop over equal-length
+  // clips) is captured into a CUDA graph and replayed from then on.
+  int opt_graphs = 1;
+  cudaStream_t host_stream = nullptr;
+  cudaEvent_t host_fence = nullptr;
+  struct GraphSlot {
+    bool seen = false;
+    int kind = -1, B = 0;
+    long long ld = 0;
+    std::vector<int> n;
+    uint64_t epoch = 0;
+    const void *audio = nullptr, *pooled = nullptr, *dec = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  } graph;
+  void drop_graph() {
+    if (graph.exec) cudaGraphExecDestroy(graph.exec);
+    graph.exec = nullptr;
+    graph.seen = false;
+  }
+
   ~ssr_engine() {
+    drop_graph();
+    if (host_fence) cudaEventDestroy(host_fence);
+    if (host_stream) cudaStreamDestroy(host_stream);
     for (void* p : owned) cudaFree(p);
   }
 };
@@ -798,8 +834,24 @@ int upload_lengths(ssr_engine* e, const int32_t* n_samples, int B, const std::ve
   std::string& err = e->err;
   if (e->nsamp_dev.ensure(sizeof(int) * B, st, err)) return -1;
   if (e->lens_dev.ensure(sizeof(int) * B, st, err)) return -1;
+  // unchanged since the previous call (the usual case in a per-clip loop): the device copies are still right
+  // (same buffers, same stream only: the earlier copy is then ordered before this call's kernels)
+  if (e->up_ptr_n == e->nsamp_dev.p && e->up_ptr_l == e->lens_dev.p && e->up_stream == st &&
+      (int)e->up_nsamp.size() == B && e->up_lens == lens &&
+      memcmp(e->up_nsamp.data(), n_samples, sizeof(int) * B) == 0)
+    return 0;
+  if (e->capturing) {  // a host-to-device copy from a stack vector must not end up inside a replayed graph
+    err = "length upload needed during graph capture";
+    return -1;
+  }
+  e->up_nsamp.clear();  // stays empty if a copy below fails
   CK(cudaMemcpyAsync(e->nsamp_dev.p, n_samples, sizeof(int) * B, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(e->lens_dev.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  e->up_nsamp.assign(n_samples, n_samples + B);
+  e->up_lens = lens;
+  e->up_ptr_n = e->nsamp_dev.p;
+  e->up_ptr_l = e->lens_dev.p;
+  e->up_stream = st;
   return 0;
 }
 
@@ -1340,10 +1392,13 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_attn_simt = value;
   else if (k == "posconv_generic")
     e->opt_posconv_generic = value;
+  else if (k == "graphs")
+    e->opt_graphs = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;
   }
+  e->drop_graph();  // a captured graph bakes the options of its capture in
   return 0;
 }
 
@@ -1393,6 +1448,81 @@ int ssr_logmel(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const in
   return whisper_logmel(e, audio_dev, audio_ld, n_samples, B, mel_dev, false, as_stream(cuda_stream));
 }
 
+// The host entry points run on a private stream (the legacy default stream cannot be captured into a graph). It is
+// ordered after everything already queued on the legacy default stream — which is where torch's default work and the
+// device entry points of a default-stream caller live — and is synchronised before the entry point returns.
+static int host_entry_stream(ssr_engine* e, cudaStream_t* out) {
+  std::string& err = e->err;
+  if (!e->host_stream) {
+    CK(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->host_fence, cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(e->host_fence, nullptr));
+  CK(cudaStreamWaitEvent(e->host_stream, e->host_fence, 0));
+  *out = e->host_stream;
+  return 0;
+}
+
+static int forward_dispatch(ssr_engine* e, int kind, const float* audio, int64_t ld, const int32_t* n, int B,
+                            float* pooled, float* dec, cudaStream_t st) {
+  return kind == 0 ? wavlm_forward(e, audio, ld, n, B, pooled, st) : whisper_forward(e, audio, ld, n, B, pooled, st, dec);
+}
+
+// Eager on the first sight of a (path, batch, pitch, lengths, buffers) signature, captured into a CUDA graph on the
+// second, replayed afterwards. Anything that could change what the captured kernels should do invalidates the slot:
+// a different signature, a workspace reallocation (arena epoch), ssr_set_option.
+static int forward_graphed(ssr_engine* e, int kind, const float* audio, int64_t ld, const int32_t* n, int B,
+                           float* pooled, float* dec, cudaStream_t st) {
+  std::string& err = e->err;
+  const bool eligible = e->opt_graphs && !e->opt_profile && e->opt_snapshot_layer < 0 && B > 0 && B <= 16;
+  if (!eligible) return forward_dispatch(e, kind, audio, ld, n, B, pooled, dec, st);
+  ssr_engine::GraphSlot& g = e->graph;
+  const bool same = g.seen && g.kind == kind && g.B == B && g.ld == ld && g.epoch == g_arena_epoch &&
+                    g.audio == audio && g.pooled == pooled && g.dec == dec &&
+                    memcmp(g.n.data(), n, sizeof(int) * B) == 0;
+  if (same && g.exec) {
+    CK(cudaGraphLaunch(g.exec, st));
+    e->launches += g.launches;
+    return 0;
+  }
+  if (same) {
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = e->launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    e->capturing = true;
+    const int rc = forward_dispatch(e, kind, audio, ld, n, B, pooled, dec, st);
+    e->capturing = false;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc == 0 && ce == cudaSuccess && graph != nullptr && g.epoch == g_arena_epoch &&
+        cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+      cudaGraphDestroy(graph);
+      g.launches = e->launches - l0;
+      CK(cudaGraphLaunch(g.exec, st));
+      return 0;
+    }
+    // capture did not work out (e.g. a first-use allocation inside): forget it and run this call eagerly
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    e->drop_graph();
+    e->launches = l0;
+    e->opt_graphs = 0;  // do not try again on this engine
+    return forward_dispatch(e, kind, audio, ld, n, B, pooled, dec, st);
+  }
+  e->drop_graph();
+  const int rc = forward_dispatch(e, kind, audio, ld, n, B, pooled, dec, st);
+  if (rc) return rc;
+  g.seen = true;
+  g.kind = kind;
+  g.B = B;
+  g.ld = ld;
+  g.n.assign(n, n + B);
+  g.epoch = g_arena_epoch;
+  g.audio = audio;
+  g.pooled = pooled;
+  g.dec = dec;
+  return 0;
+}
+
 static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
                     int32_t B, float* pooled_host) {
   std::string& err = e->err;
@@ -1403,14 +1533,14 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
   if (B == 0) return 0;
   cudaSetDevice(e->device);
   cudaStream_t st = nullptr;
+  if (host_entry_stream(e, &st)) return -1;
   const size_t in_bytes = (size_t)B * audio_ld * 4;
   const size_t out_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
   if (e->audio_stage.ensure(in_bytes, st, err)) return -1;
   if (e->pooled_stage.ensure(out_bytes, st, err)) return -1;
   CK(cudaMemcpyAsync(e->audio_stage.p, audio_host, in_bytes, cudaMemcpyHostToDevice, st));
-  int rc = wavlm ? wavlm_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B, e->pooled_stage.as<float>(), st)
-                 : whisper_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B,
-                                   e->pooled_stage.as<float>(), st);
+  int rc = forward_graphed(e, wavlm ? 0 : 1, e->audio_stage.as<float>(), audio_ld, n_samples, B,
+                           e->pooled_stage.as<float>(), nullptr, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(pooled_host, e->pooled_stage.p, out_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -1469,6 +1599,7 @@ int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_
   if (B == 0) return 0;
   cudaSetDevice(e->device);
   cudaStream_t st = nullptr;
+  if (host_entry_stream(e, &st)) return -1;
   const size_t in_bytes = (size_t)B * audio_ld * 4;
   const size_t enc_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
   const size_t dec_bytes = (size_t)B * (e->dec_L + 1) * e->d.hidden * 4;
@@ -1477,7 +1608,11 @@ int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_
   float* enc_dev = e->pooled_stage.as<float>();
   float* dec_dev = reinterpret_cast<float*>(reinterpret_cast<char*>(e->pooled_stage.p) + enc_bytes);
   CK(cudaMemcpyAsync(e->audio_stage.p, audio_host, in_bytes, cudaMemcpyHostToDevice, st));
-  if (whisper_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B, enc_dev, st, dec_dev)) return -1;
+  if (e->dec_L == 0) {
+    err = "this Whisper engine was created without decoder weights";
+    return -1;
+  }
+  if (forward_graphed(e, 1, e->audio_stage.as<float>(), audio_ld, n_samples, B, enc_dev, dec_dev, st)) return -1;
   CK(cudaMemcpyAsync(pooled_host, enc_dev, enc_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(dec_host, dec_dev, dec_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -31,6 +31,12 @@ def _as_f32_clip(a) -> np.ndarray:
     return np.ascontiguousarray(a)
 
 
+def row_pitch(t: torch.Tensor) -> int:
+    """Elements between consecutive rows of a 2-D tensor. A single-row view (e.g. `x[None]`) may carry stride 0 or any
+    other value in its size-1 dimension; the C ABI wants a pitch that covers the row."""
+    return int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
+
+
 class _EngineBase:
     family = -1
 
@@ -127,7 +133,7 @@ class _EngineBase:
     def _call_dev(self, fn, audio: torch.Tensor, n_samples: np.ndarray, out: torch.Tensor, stream=None):
         n_samples = np.ascontiguousarray(n_samples, dtype=np.int32)
         st = torch.cuda.current_stream(self.device) if stream is None else stream
-        rc = fn(self._h, audio.data_ptr(), audio.stride(0), n_samples.ctypes.data_as(_lib.c_i32p), audio.shape[0],
+        rc = fn(self._h, audio.data_ptr(), row_pitch(audio), n_samples.ctypes.data_as(_lib.c_i32p), audio.shape[0],
                 out.data_ptr(), st.cuda_stream)
         if rc != 0:
             raise SsrError(self._err())
@@ -149,7 +155,7 @@ class _EngineBase:
         assert not audio_host.is_cuda and audio_host.dtype == torch.float32 and audio_host.stride(1) == 1
         assert not out_host.is_cuda and out_host.dtype == torch.float32 and out_host.is_contiguous()
         n = np.ascontiguousarray(n_samples, dtype=np.int32)
-        rc = self._pooled_host_fn(self._h, audio_host.data_ptr(), audio_host.stride(0), n.ctypes.data_as(_lib.c_i32p),
+        rc = self._pooled_host_fn(self._h, audio_host.data_ptr(), row_pitch(audio_host), n.ctypes.data_as(_lib.c_i32p),
                                   audio_host.shape[0], out_host.data_ptr())
         if rc != 0:
             raise SsrError(self._err())

@@ -405,6 +405,58 @@ def test_engine_lifecycle_releases_device_memory():
         eng.pooled(clips)  # a closed engine must fail loudly, not crash
 
 
+def test_graph_replay_of_repeated_small_batches():
+    """The host entry points capture a CUDA graph on the second identical (batch, pitch, lengths) call and replay it
+    afterwards: results must be bit-identical to eager execution, for new audio of the same shape, across signature
+    changes (new lengths -> eager -> capture again), option changes and for the Whisper decoder path."""
+    from ssr_b200 import synth
+
+    _, _, eng = wavlm("tiny_stable")
+    a = [synth.clip_by_index(i, 16000) for i in range(8)]
+    eng.set_option("graphs", 0)
+    want = [eng.pooled([c]) for c in a]
+    want_pair = eng.pooled([a[0][:12000], a[1]])
+    eng.set_option("graphs", 1)
+    l0 = eng.launch_count
+    got = [eng.pooled([c]) for c in a]           # eager, capture, then six replays
+    per_call = (eng.launch_count - l0) // len(a)
+    assert per_call > 20                          # replays are counted like eager launches
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+    np.testing.assert_array_equal(eng.pooled([a[0][:12000], a[1]]), want_pair)   # new signature: eager
+    np.testing.assert_array_equal(eng.pooled([a[0][:12000], a[1]]), want_pair)   # capture
+    np.testing.assert_array_equal(eng.pooled([a[0][:12000], a[1]]), want_pair)   # replay
+    np.testing.assert_array_equal(eng.pooled([a[3]]), want[3])                   # back to the first signature
+    eng.set_option("fused_pool", 0)               # option change drops the graph
+    unfused = eng.pooled([a[3]])
+    eng.set_option("fused_pool", 1)
+    np.testing.assert_allclose(unfused, want[3], rtol=0, atol=2e-6 * np.abs(want[3]).max())
+    np.testing.assert_array_equal(eng.pooled([a[3]]), want[3])
+    big = eng.pooled(a * 3)                       # 24 clips: above the graph limit, and grows the workspace
+    np.testing.assert_allclose(big[:8], np.concatenate(want), rtol=0, atol=2e-6 * np.abs(big).max())
+    np.testing.assert_array_equal(eng.pooled([a[5]]), want[5])
+    np.testing.assert_array_equal(eng.pooled([a[6]]), want[6])
+    np.testing.assert_array_equal(eng.pooled([a[7]]), want[7])
+
+
+def test_single_row_views_with_degenerate_stride():
+    """`x[None]` of a 1-D array has stride 0 in its size-1 dimension; the shim must still hand the C ABI a row pitch."""
+    import torch
+
+    from ssr_b200 import synth
+
+    _, _, eng = wavlm("tiny_stable")
+    clip = synth.clip_by_index(7, 16000)
+    want = eng.pooled([clip])
+    dev = torch.from_numpy(clip[None]).cuda()
+    assert dev.stride(0) in (0, 16000)
+    got = eng.pooled_device(dev, [16000]).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    host = torch.from_numpy(clip[None])
+    out = torch.empty((1, eng.layers + 1, eng.hidden))
+    np.testing.assert_array_equal(eng.pooled_pinned(host, [16000], out).numpy(), want)
+
+
 def test_pooled_stream_matches_synchronous_calls():
     """The streaming API (copies overlapped with neighbouring batches on side streams) returns, in order, exactly what
     the synchronous host call returns — including a shorter last batch and a change of clip length."""
