@@ -209,13 +209,183 @@ wavlm_conv0_kernel(const Conv0Args a) {
   }
 }
 
+// ------------------------------------------------------------------------------- conv layer 0 on the tensor cores
+// LayerNorm variant (feat_extract_norm = "layer", WavLM-Large). The step is power-limited and this layer was 1.5e9
+// warp instructions of CUDA-core work per 256 clips (10 FMA per output element before the norm even starts), so the
+// 10-tap products move to mma.sync without giving up fp32 accuracy: x and w are each split into bf16 hi + lo parts
+// and   x.w ~= xh.wh + xl.wh + xh.wl   is one K = 32 contraction   [xh(10) | xl(10) | xh(10) | 0 0] . [wh; wh; wl; 0]
+// (relative error ~2^-16, the dropped xl.wl term). LayerNorm needs the whole 512-channel row, which would be 256
+// accumulator registers per thread; instead the products are formed twice: pass 1 keeps only sum / sum of squares,
+// pass 2 normalises, applies GELU and stores through a small per-warp staging tile (128-byte row segments).
+constexpr int C0M_WARPS = 8;
+constexpr int C0M_FRAMES = 16 * C0M_WARPS;  // frames per block iteration
+constexpr int C0M_WP = 40;                  // bf16 pitch of a weight row (80 bytes: conflict-free fragment loads)
+constexpr int C0M_SP = 72;                  // bf16 pitch of a staging row (64 channels + pad)
+constexpr int C0M_XLEN = C0M_FRAMES * 5 + 8;
+constexpr int C0M_OFF_GB = 512 * C0M_WP * 2;
+constexpr int C0M_OFF_STAGE = C0M_OFF_GB + 2 * 512 * 4;
+constexpr int C0M_OFF_X = C0M_OFF_STAGE + C0M_WARPS * 16 * C0M_SP * 2;
+constexpr int C0M_SMEM = C0M_OFF_X + 2 * C0M_XLEN * 2;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256)
+wavlm_conv0_mma_kernel(const Conv0Args a, const int iters) {
+  extern __shared__ __align__(16) unsigned char c0m_smem[];
+  bf16* w_s = reinterpret_cast<bf16*>(c0m_smem);                                   // [channel][k = 0..31] (+ pad)
+  float* gb_s = reinterpret_cast<float*>(c0m_smem + C0M_OFF_GB);                   // gamma | beta
+  bf16* stage_all = reinterpret_cast<bf16*>(c0m_smem + C0M_OFF_STAGE);             // [warp][16][C0M_SP]
+  bf16* xh_s = reinterpret_cast<bf16*>(c0m_smem + C0M_OFF_X);
+  bf16* xl_s = xh_s + C0M_XLEN;
+  const int b = blockIdx.y;
+  const int n = a.n_samples[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+
+  // weights: k 0-9 -> hi, 10-19 -> hi, 20-29 -> lo, 30-31 -> 0
+  for (int i = threadIdx.x; i < 512 * 32; i += 256) {
+    const int ch = i >> 5, k = i & 31;
+    float v = 0.f;
+    if (k < 30) {
+      const float w = a.w[ch * 10 + (k % 10)];
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      v = k < 20 ? hi : w - hi;
+    }
+    w_s[ch * C0M_WP + k] = __float2bfloat16_rn(v);
+  }
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    gb_s[i] = a.gamma[i];
+    gb_s[512 + i] = a.beta[i];
+  }
+  const float mean = a.stats[2 * b], rstd = a.stats[2 * b + 1];
+  const float* x = a.audio + (long long)b * a.audio_ld;
+
+  for (int it = 0; it < iters; ++it) {
+    const int t_blk = (blockIdx.x * iters + it) * C0M_FRAMES;
+    if (t_blk >= a.slot0) break;  // block-uniform
+    __syncthreads();              // previous iteration's readers of xh_s / xl_s are done
+    for (int i = threadIdx.x; i < C0M_FRAMES * 5 + 5; i += 256) {
+      const int idx = t_blk * 5 + i;
+      const float v = (idx < n) ? (x[idx] - mean) * rstd : 0.f;
+      const bf16 hi = __float2bfloat16_rn(v);
+      xh_s[i] = hi;
+      xl_s[i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    __syncthreads();
+
+    // A fragments of this warp's 16 frames: rows g and g + 8, two k-steps
+    const int f0 = warp * 16;
+    uint32_t af[2][4];
+    {
+      auto pair = [&](int frame, int k) -> uint32_t {  // k even; the pair never straddles a segment (10, 20, 30 are even)
+        if (k >= 30) return 0u;
+        const bf16* src = k < 10 ? xh_s + frame * 5 + k : k < 20 ? xl_s + frame * 5 + (k - 10)
+                                                                 : xh_s + frame * 5 + (k - 20);
+        const uint32_t lo = __bfloat16_as_ushort(src[0]), hi = __bfloat16_as_ushort(src[1]);
+        return lo | (hi << 16);
+      };
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        af[ks][0] = pair(f0 + g, ks * 16 + 2 * c);
+        af[ks][1] = pair(f0 + g + 8, ks * 16 + 2 * c);
+        af[ks][2] = pair(f0 + g, ks * 16 + 2 * c + 8);
+        af[ks][3] = pair(f0 + g + 8, ks * 16 + 2 * c + 8);
+      }
+    }
+    auto tile = [&](int nt, float (&acc)[4]) {
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      const bf16* wrow = w_s + (nt * 8 + g) * C0M_WP + 2 * c;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma16816(acc, af[ks], *reinterpret_cast<const uint32_t*>(wrow + ks * 16),
+                 *reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8));
+    };
+
+    // pass 1: row statistics
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 4
+    for (int nt = 0; nt < 64; ++nt) {
+      float acc[4];
+      tile(nt, acc);
+      s0 += acc[0] + acc[1];
+      q0 = fmaf(acc[0], acc[0], fmaf(acc[1], acc[1], q0));
+      s1 += acc[2] + acc[3];
+      q1 = fmaf(acc[2], acc[2], fmaf(acc[3], acc[3], q1));
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    const float mu0 = s0 * (1.0f / 512.f), mu1 = s1 * (1.0f / 512.f);
+    const float rs0 = rsqrtf(fmaxf(q0 * (1.0f / 512.f) - mu0 * mu0, 0.f) + 1e-5f);
+    const float rs1 = rsqrtf(fmaxf(q1 * (1.0f / 512.f) - mu1 * mu1, 0.f) + 1e-5f);
+
+    // pass 2: normalise, GELU, store 64 channels (one 128-byte segment per frame) at a time
+    bf16* stg = stage_all + warp * (16 * C0M_SP);
+    for (int grp = 0; grp < 8; ++grp) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int nt = grp * 8 + j;
+        float acc[4];
+        tile(nt, acc);
+        const int ch = nt * 8 + 2 * c;
+        const float2 ga = *reinterpret_cast<const float2*>(&gb_s[ch]);
+        const float2 be = *reinterpret_cast<const float2*>(&gb_s[512 + ch]);
+        const float y00 = gelu_fast(fmaf((acc[0] - mu0) * rs0, ga.x, be.x));
+        const float y01 = gelu_fast(fmaf((acc[1] - mu0) * rs0, ga.y, be.y));
+        const float y10 = gelu_fast(fmaf((acc[2] - mu1) * rs1, ga.x, be.x));
+        const float y11 = gelu_fast(fmaf((acc[3] - mu1) * rs1, ga.y, be.y));
+        *reinterpret_cast<__nv_bfloat162*>(stg + g * C0M_SP + j * 8 + 2 * c) = __floats2bfloat162_rn(y00, y01);
+        *reinterpret_cast<__nv_bfloat162*>(stg + (g + 8) * C0M_SP + j * 8 + 2 * c) = __floats2bfloat162_rn(y10, y11);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {  // 16 rows x 128 bytes = 128 uint4, four per lane
+        const int idx = r * 32 + lane, row = idx >> 3, seg = idx & 7;
+        const int t = t_blk + f0 + row;
+        if (t < a.slot0)
+          *reinterpret_cast<uint4*>(a.out + ((long long)b * a.slot0 + t) * 512 + grp * 64 + seg * 8) =
+              *reinterpret_cast<const uint4*>(stg + row * C0M_SP + seg * 8);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+static bool conv0_fma_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSR_CONV0_FMA");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 }  // namespace
 
 int launch_wavlm_conv0(const Conv0Args& a, cudaStream_t st, std::string& err) {
   if (a.B <= 0) return 0;
   wave_stats_kernel<<<a.B, 512, 0, st>>>(a.audio, a.audio_ld, a.n_samples, a.stats, a.do_normalize);
   dim3 grid(ceil_div(a.slot0, C0_FRAMES), a.B);
-  if (a.mode == 0) {
+  if (a.mode == 0 && !conv0_fma_forced()) {
+    // each block walks `iters` groups of 128 frames so that the 40 KB weight image is built once per ~512 frames
+    const int groups = ceil_div(a.slot0, C0M_FRAMES);
+    const int iters = groups >= 4 ? 4 : groups;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(wavlm_conv0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0M_SMEM);
+      attr_set = true;
+    }
+    wavlm_conv0_mma_kernel<<<dim3(ceil_div(groups, iters), a.B), 256, C0M_SMEM, st>>>(a, iters);
+  } else if (a.mode == 0) {
     wavlm_conv0_kernel<0><<<grid, 256, 0, st>>>(a);
   } else {
     cudaMemsetAsync(a.gn_acc, 0, sizeof(double) * 1024 * a.B, st);
