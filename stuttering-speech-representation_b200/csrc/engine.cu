@@ -144,7 +144,7 @@ struct ssr_engine {
 
   // ---- workspace ----
   Buf nsamp_dev, lens_dev, stats, gn_acc;
-  Buf conv[7], feat_ln, feat, xp, posconv, h, tmp, xn, qkv, ctx, mid, gate, pool_part;
+  Buf conv[7], feat_ln, feat, xp, posconv, h, tmp, xn, qkv, ctx, mid, gate, pool_part, pool_layers;
   Buf logspec, gmax, conv_in, c1, lens1500;
   Buf audio_stage, pooled_stage;
   Buf snap[8];
@@ -663,6 +663,14 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
   float* gate = wavlm ? e->gate.as<float>() : nullptr;
   float* part = e->pool_part.as<float>();
   const bool fused = e->opt_fused_pool && slot >= 32;
+  // pre-LN stacks: every layer's output projection leaves its pooling partials in its own slice, and ONE finalize
+  // launch after the loop reduces all of them (23 / 31 tiny launches otherwise)
+  const size_t part_stride = (size_t)ceil_div(M, 32) * 2 * D;
+  float* part_layers = nullptr;
+  if (pre_ln && fused && L > 1) {
+    if (e->pool_layers.ensure((size_t)(L - 1) * part_stride * 4, st, err)) return -1;
+    part_layers = e->pool_layers.as<float>();
+  }
 
   for (int l = 0; l < L; ++l) {
     const LayerW& W = e->layers[l];
@@ -737,21 +745,19 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
       EpiParams ep = epi_plain(W.b2, ACT_NONE, h, D, h, D, nullptr, 0);
       const bool pool_here = (l < L - 1);  // hidden_states[l+1] = this layer's output (the last one is LN'd first)
       if (pool_here && fused) {
-        ep.pool_part = part;
+        ep.pool_part = part_layers + (size_t)l * part_stride;
         ep.pool_slot = slot;
         ep.lens = lens;
       }
       if (run_gemm(e, linear_op(mid, M, F, W.w2, D, ep), st, "gemm_ffn2")) return -1;
       if (snap && snapshot(e, 6, "L.h_out", h, 0, M, D, st)) return -1;
-      if (pool_here) {
-        if (fused) {
-          e->launches++;
-          ProfScope ps(e, st, "pool_finalize");
-          if (launch_pool_finalize(part, B, slot, D, lens, pooled + (long long)(l + 1) * D, (long long)L1 * D, st, err))
-            return -1;
-        } else if (pool_into(e, h, B, slot, D, pooled, l + 1, L1, st)) {
+      if (pool_here && !fused && pool_into(e, h, B, slot, D, pooled, l + 1, L1, st)) return -1;
+      if (fused && l == L - 2) {  // the last pooled-here layer is done: hidden_states[1 .. L-1] in one launch
+        e->launches++;
+        ProfScope ps(e, st, "pool_finalize");
+        if (launch_pool_finalize(part_layers, B, slot, D, lens, pooled + D, (long long)L1 * D, st, err, L - 1,
+                                 (long long)part_stride, (long long)D))
           return -1;
-        }
       }
     } else {
       // post-LN (WavLM Base+)

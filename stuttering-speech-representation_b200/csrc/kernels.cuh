@@ -31,7 +31,8 @@ int launch_layernorm(const LayerNormArgs& a, cudaStream_t st, std::string& err);
 int launch_pool_mean(const float* x, int B, int slot, int D, const int* lens, float* out, long long out_stride,
                      cudaStream_t st, std::string& err);
 int launch_pool_finalize(const float* part, int B, int slot, int D, const int* lens, float* out, long long out_stride,
-                         cudaStream_t st, std::string& err);
+                         cudaStream_t st, std::string& err, int n_layers = 1, long long part_layer_stride = 0,
+                         long long out_layer_stride = 0);
 int launch_posconv_pack(const float* x, int B, int slot, int D, const int* lens, bf16* xp, int pslot, cudaStream_t st,
                         std::string& err);
 int launch_posconv_finish(const float* conv, int pslot, const float* bias, const float* x, int B, int slot, int D,

@@ -206,7 +206,11 @@ int launch_pool_mean(const float* x, int B, int slot, int D, const int* lens, fl
 // Reduce the per-32-row-group partial column sums written by the GEMM epilogue (fixed order -> deterministic).
 __global__ void __launch_bounds__(128)
 pool_finalize_kernel(const float* __restrict__ part, int slot, int D, const int* __restrict__ lens,
-                     float* __restrict__ out, long long out_stride) {
+                     float* __restrict__ out, long long out_stride, long long part_layer_stride,
+                     long long out_layer_stride) {
+  // blockIdx.z = layer: the partial sums of several layers are reduced by one launch
+  part += (long long)blockIdx.z * part_layer_stride;
+  out += (long long)blockIdx.z * out_layer_stride;
   const int b = blockIdx.y;
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= D) return;
@@ -225,9 +229,12 @@ pool_finalize_kernel(const float* __restrict__ part, int slot, int D, const int*
 }
 
 int launch_pool_finalize(const float* part, int B, int slot, int D, const int* lens, float* out, long long out_stride,
-                         cudaStream_t st, std::string& err) {
-  dim3 grid(ceil_div(D, 128), B);
-  pool_finalize_kernel<<<grid, 128, 0, st>>>(part, slot, D, lens, out, out_stride);
+                         cudaStream_t st, std::string& err, int n_layers, long long part_layer_stride,
+                         long long out_layer_stride) {
+  if (n_layers <= 0) return 0;
+  dim3 grid(ceil_div(D, 128), B, n_layers);
+  pool_finalize_kernel<<<grid, 128, 0, st>>>(part, slot, D, lens, out, out_stride, part_layer_stride,
+                                             out_layer_stride);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("pool finalize launch: ") + cudaGetErrorString(ce);
