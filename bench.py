@@ -41,15 +41,47 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and throttle reasons sampled DURING the timed region: NVML polled every few milliseconds from a
+    thread (the timed region of a default run is ~0.4 s, too short for `nvidia-smi -lms`, which is the fallback)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
         "clocks_event_reasons.sw_power_cap"
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.stop_flag, self.th = None, [], False, None
+
+    def _nvml_loop(self, h):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.nvml = nv
+            self.th = threading.Thread(target=self._nvml_loop, args=(h,), daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
@@ -64,6 +96,18 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=2)
+            sm = [s[0] for s in self.samples]
+            pw = [s[1] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= int(s[2])
+            reasons = sorted(k for k, b in self.REASON_BITS.items() if bits & b)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.mx,
+                    "power_w_max": round(max(pw), 2) if pw else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -87,7 +131,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 def dist_env():
