@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libssr_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["gemm.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "frontend.cu", "decoder.cu", "augment.cu", "head.cu", "engine.cu"]
+SOURCES = ["gemm.cu", "gemm_ln.cu", "rowops.cu", "attention.cu", "attention_tc.cu", "frontend.cu", "decoder.cu", "augment.cu", "head.cu", "engine.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "ptx.cuh", os.path.join("..", "..", "include", "ssr_b200.h")]
 
 NVCC_FLAGS = [

@@ -113,6 +113,7 @@ struct ssr_engine {
   // options
   int opt_simt = 0, opt_fused_pool = 1, opt_snapshot_layer = -1, opt_profile = 0, opt_attn_simt = 0;
   int opt_posconv_generic = 0;  // 1: positional conv through the generic GEMM kernel (cross-check)
+  int opt_conv_ln_fused = 1;    // 1: WavLM-Large conv layers 1-6 as conv + LayerNorm + GELU in one kernel (gemm_ln.cu)
   std::vector<ProfEntry> prof;
   std::string prof_json;
 
@@ -961,6 +962,17 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     op.a_mode = 0;
     op.a_cols = 0;
     const bool ln = d.feat_norm == SSR_FEAT_NORM_LAYER;
+    if (ln && e->opt_conv_ln_fused && !e->opt_simt) {
+      e->launches++;
+      ProfScope ps(e, st, "gemm_conv_ln", 2.0 * (double)Mi * 512.0 * (double)op.K);
+      if (launch_gemm_ln(op.A, op.lda, op.a_rows, op.W, Mi, op.K, e->cln_g[i], e->cln_b[i], 1e-5f,
+                         e->conv[i].as<bf16>(), st, e->num_sms, err))
+        return -1;
+      char nm[16];
+      snprintf(nm, sizeof nm, "conv%d", i);
+      reg_dbg(e, nm, e->conv[i].p, 1, B, slots[i], 512);
+      continue;
+    }
     op.epi = epi_plain(nullptr, ln ? ACT_NONE : ACT_GELU, nullptr, 0, nullptr, 0, e->conv[i].as<bf16>(), 512);
     if (run_gemm(e, op, st, "gemm_conv")) return -1;
     if (ln) {
@@ -1400,6 +1412,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_posconv_generic = value;
   else if (k == "graphs")
     e->opt_graphs = value;
+  else if (k == "conv_ln_fused")
+    e->opt_conv_ln_fused = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;

@@ -88,6 +88,10 @@ struct Conv0Args {
 };
 int launch_wavlm_conv0(const Conv0Args& a, cudaStream_t st, std::string& err);
 
+// Conv1d (implicit GEMM, 512 output channels) + LayerNorm(512) + GELU in one kernel (gemm_ln.cu).
+int launch_gemm_ln(const bf16* A, long long lda, long long a_rows, const bf16* W, int M, int K, const float* gamma,
+                   const float* beta, float eps, bf16* out, cudaStream_t st, int num_sms, std::string& err);
+
 // Whisper log-mel front end.
 struct LogMelArgs {
   const float* audio;

@@ -123,6 +123,15 @@ def test_wavlm_vs_oracle_and_variants(name):
     mma = eng.pooled(clips)
     eng.set_option("attn_simt", 0)
     check_pooled(mma, base, f"{name} tcgen05 vs mma.sync attention", cos_min=0.99999, rel_max=8e-3)
+    eng.set_option("conv_ln_fused", 0)  # conv GEMM + separate LayerNorm/GELU row kernel instead of the 4-CTA fused one
+    unfused_conv = eng.pooled(clips)
+    taps_unfused = {k: eng.debug_fetch(k) for k in ("conv1", "conv6")}
+    eng.set_option("conv_ln_fused", 1)
+    check_pooled(unfused_conv, base, f"{name} fused vs two-kernel conv + LayerNorm", cos_min=0.99999, rel_max=8e-3)
+    eng.pooled(clips)
+    for k, ref_tap in taps_unfused.items():
+        got_tap = eng.debug_fetch(k)
+        assert np.abs(got_tap.astype(np.float64) - ref_tap).max() <= 0.02 * max(1.0, np.abs(ref_tap).max()), k
 
 
 def test_trained_like_statistics_vs_oracle():
