@@ -17,7 +17,7 @@ PROF = os.path.join(ROOT, "profiles")
 
 
 def group_of(name: str) -> str:
-    if "gemm_tc" in name or "posconv_tc" in name or name.startswith("gemm"):
+    if "gemm_tc" in name or "gemm_ln" in name or "posconv_tc" in name or name.startswith("gemm"):
         return "gemm (tcgen05)"
     if "attention" in name:
         return "attention"
