@@ -47,6 +47,64 @@ dec_qproj_kernel(const float* __restrict__ q, const bf16* __restrict__ wk, float
   }
 }
 
+// ------------------------------------------------------------------------------------------------ token GEMV
+// out[m, n] = act(A[m, :] . W[n, :] + bias[n]) (+ resid[m, n]) for a handful of token rows (M <= 16: the per-clip and
+// small-batch decoder probe). A 128 x 256 tensor-core tile would hold one live row and a couple of CTAs would stream
+// the whole weight matrix; here every warp owns one output column and the grid covers the SMs, so the weights stream
+// at HBM speed (the only traffic that matters: 3.3 - 13 MB of bf16 per Linear).
+constexpr int GV_MMAX = 16;
+__global__ void __launch_bounds__(256)
+dec_gemv_kernel(const bf16* __restrict__ A, int M, int K, const bf16* __restrict__ W, int N,
+                const float* __restrict__ bias, int act, const float* resid, int ldr, float* out_f32, int ldo32,
+                bf16* __restrict__ out_bf16, int ldo16) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[GV_MMAX];
+#pragma unroll
+  for (int m = 0; m < GV_MMAX; ++m) acc[m] = 0.f;
+  const bf16* wrow = W + (long long)n * K;
+  for (int k0 = lane * 8; k0 < K; k0 += 256) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(wrow + k0);
+    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+    float wf[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wf[2 * i] = __low2float(w2[i]);
+      wf[2 * i + 1] = __high2float(w2[i]);
+    }
+#pragma unroll
+    for (int m = 0; m < GV_MMAX; ++m) {
+      if (m < M) {
+        const uint4 av = *reinterpret_cast<const uint4*>(A + (long long)m * K + k0);
+        const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[m] = fmaf(wf[2 * i], __low2float(a2[i]), acc[m]);
+          acc[m] = fmaf(wf[2 * i + 1], __high2float(a2[i]), acc[m]);
+        }
+      }
+    }
+  }
+  float mine = 0.f;  // lane m keeps row m's sum
+#pragma unroll
+  for (int m = 0; m < GV_MMAX; ++m) {
+    if (m < M) {  // warp-uniform
+      float v = acc[m];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == m) mine = v;
+    }
+  }
+  if (lane < M) {
+    float v = mine + (bias ? bias[n] : 0.f);
+    if (act == ACT_GELU) v = gelu_fast(v);
+    if (resid) v += resid[(long long)lane * ldr + n];
+    if (out_f32) out_f32[(long long)lane * ldo32 + n] = v;
+    if (out_bf16) out_bf16[(long long)lane * ldo16 + n] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ fused pass
 constexpr int XC_ROWS = 16;    // encoder rows per chunk (= MMA M of the score GEMM, K of the context GEMM)
 constexpr int XC_STAGES = 3;
@@ -327,6 +385,24 @@ int launch_xattn(const CUtensorMap& tme, const DecCrossArgs& a, int S, int R, cu
 }
 
 }  // namespace
+
+bool dec_gemv_applicable(int M, int K) { return M >= 1 && M <= GV_MMAX && K % 8 == 0; }
+
+int launch_dec_gemv(const bf16* A, int M, int K, const bf16* W, int N, const EpiParams& ep, cudaStream_t st,
+                    std::string& err) {
+  if (!dec_gemv_applicable(M, K) || ep.in_slot != 0 || ep.pool_part != nullptr || ep.resid_by_t) {
+    err = "decoder GEMV: unsupported shape or epilogue";
+    return -1;
+  }
+  dec_gemv_kernel<<<ceil_div(N, 8), 256, 0, st>>>(A, M, K, W, N, ep.bias, ep.act, ep.resid, ep.ldr, ep.out_f32,
+                                                   ep.ldo32, ep.out_bf16, ep.ldo16);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    err = std::string("decoder GEMV launch: ") + cudaGetErrorString(ce);
+    return -1;
+  }
+  return 0;
+}
 
 int launch_bcast_rows(const float* v, float* out, int B, int D, long long ld, cudaStream_t st, std::string& err) {
   dim3 grid(ceil_div(D, 256), B);

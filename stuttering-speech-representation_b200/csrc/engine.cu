@@ -1184,6 +1184,16 @@ int whisper_decoder_token(ssr_engine* e, int B, float* dec_out, cudaStream_t st)
     return 0;
   };
 
+  // token-level Linear: a handful of rows stream the weights through the GEMV kernel, larger batches use the
+  // tensor-core GEMM
+  const bool small = dec_gemv_applicable(B, D) && dec_gemv_applicable(B, Fd) && !e->opt_simt;
+  auto lin = [&](const bf16* A, int K, const bf16* Wt, int N, const EpiParams& ep) -> int {
+    if (!small) return run_gemm(e, linear_op(A, B, K, Wt, N, ep), st, "gemm_dec");
+    e->launches++;
+    ProfScope ps(e, st, "gemv_dec", 2.0 * (double)B * (double)N * (double)K);
+    return launch_dec_gemv(A, B, K, Wt, N, ep, st, err);
+  };
+
   e->launches++;
   if (launch_bcast_rows(e->dec_h0, h, B, D, D, st, err)) return -1;
   if (save_state(0)) return -1;
@@ -1191,17 +1201,11 @@ int whisper_decoder_token(ssr_engine* e, int B, float* dec_out, cudaStream_t st)
     const DecLayerW& W = e->dec_layers[l];
     // self-attention over a single token == out_proj(v_proj(LN(h)))
     if (ln(W.ln1_g, W.ln1_b, nullptr, 0, x)) return -1;
-    if (run_gemm(e, linear_op(x, B, D, W.w_sv, D, epi_plain(W.b_sv, ACT_NONE, nullptr, 0, nullptr, 0, t1, D)), st,
-                 "gemm_dec"))
-      return -1;
-    if (run_gemm(e, linear_op(t1, B, D, W.w_so, D, epi_plain(W.b_so, ACT_NONE, h, D, h, D, nullptr, 0)), st,
-                 "gemm_dec"))
-      return -1;
+    if (lin(x, D, W.w_sv, D, epi_plain(W.b_sv, ACT_NONE, nullptr, 0, nullptr, 0, t1, D))) return -1;
+    if (lin(t1, D, W.w_so, D, epi_plain(W.b_so, ACT_NONE, h, D, h, D, nullptr, 0))) return -1;
     // cross-attention over the 1500 encoder states
     if (ln(W.ln2_g, W.ln2_b, nullptr, 0, x)) return -1;
-    if (run_gemm(e, linear_op(x, B, D, W.w_cq, D, epi_plain(W.b_cq, ACT_NONE, nullptr, 0, q, D, nullptr, 0)), st,
-                 "gemm_dec"))
-      return -1;
+    if (lin(x, D, W.w_cq, D, epi_plain(W.b_cq, ACT_NONE, nullptr, 0, q, D, nullptr, 0))) return -1;
     {
       DecCrossArgs a;
       a.q = q;
@@ -1221,17 +1225,11 @@ int whisper_decoder_token(ssr_engine* e, int B, float* dec_out, cudaStream_t st)
       ProfScope ps(e, st, "dec_cross_attention", 4.0 * (double)B * H * T * D);
       if (launch_dec_cross_attention(a, st, err)) return -1;
     }
-    if (run_gemm(e, linear_op(cv, B, D, W.w_co, D, epi_plain(W.b_co, ACT_NONE, h, D, h, D, nullptr, 0)), st,
-                 "gemm_dec"))
-      return -1;
+    if (lin(cv, D, W.w_co, D, epi_plain(W.b_co, ACT_NONE, h, D, h, D, nullptr, 0))) return -1;
     // feed-forward
     if (ln(W.ln3_g, W.ln3_b, nullptr, 0, x)) return -1;
-    if (run_gemm(e, linear_op(x, B, D, W.w1, Fd, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, Fd)), st,
-                 "gemm_dec"))
-      return -1;
-    if (run_gemm(e, linear_op(mid, B, Fd, W.w2, D, epi_plain(W.b2, ACT_NONE, h, D, h, D, nullptr, 0)), st,
-                 "gemm_dec"))
-      return -1;
+    if (lin(x, D, W.w1, Fd, epi_plain(W.b1, ACT_GELU, nullptr, 0, nullptr, 0, mid, Fd))) return -1;
+    if (lin(mid, Fd, W.w2, D, epi_plain(W.b2, ACT_NONE, h, D, h, D, nullptr, 0))) return -1;
     if (l < Ld - 1 && save_state(l + 1)) return -1;
   }
   // hidden_states[Ld] = decoder.layer_norm(h), written straight into its output slot

@@ -69,6 +69,10 @@ struct DecCrossArgs {
 int launch_dec_cross_attention(const DecCrossArgs& a, cudaStream_t st, std::string& err);
 int dec_cross_splits(int B, int T, int num_sms);  // row splits per clip (scratch sizing)
 int launch_bcast_rows(const float* v, float* out, int B, int D, long long ld, cudaStream_t st, std::string& err);
+// Token-level Linear for a handful of rows (M <= 16): one warp per output column, weights streamed once.
+bool dec_gemv_applicable(int M, int K);
+int launch_dec_gemv(const bf16* A, int M, int K, const bf16* W, int N, const EpiParams& ep, cudaStream_t st,
+                    std::string& err);
 
 // WavLM waveform statistics + first conv layer (C_in = 1, k = 10, stride 5) fused with its normalisation + GELU.
 struct Conv0Args {
