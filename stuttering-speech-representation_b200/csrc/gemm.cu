@@ -959,6 +959,13 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, s
     p.num_n_tiles = op.N / 64;
     return launch_tc<64>(op, p, stream, num_sms, err);
   }
+  // Few rows (the per-clip calls: M = 150 for one 3 s clip): 256-column tiles would leave all but N / 256 SM pairs
+  // idle while each of them walks the whole K dimension; 64-column single-CTA tiles spread the weight matrix over
+  // N / 64 SMs instead. The cut-over is where the big tiles start to fill the machine.
+  if ((long long)ceil_div(op.M, 256) * (op.N / 64) <= 2LL * num_sms && op.M <= 1024) {
+    p.num_n_tiles = op.N / 64;
+    return launch_tc<64>(op, p, stream, num_sms, err);
+  }
   if (op.N % 256 == 0 && !force_single_cta()) {
     p.num_m_tiles = ceil_div(op.M, 256);
     p.num_n_tiles = op.N / 256;
