@@ -966,6 +966,12 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, s
     p.num_n_tiles = op.N / 64;
     return launch_tc<64>(op, p, stream, num_sms, err);
   }
+  // Less than one wave of 256 x 256 pair tiles (e.g. one 30 s Whisper window, M = 1500, N = 1280: 30 tiles for 74 SM
+  // pairs): 128 x 128 single-CTA tiles fill the machine better.
+  if (op.N % 256 == 0 && (long long)ceil_div(op.M, 256) * (op.N / 256) < num_sms / 2 && !force_single_cta()) {
+    p.num_n_tiles = op.N / 128;
+    return launch_tc<128>(op, p, stream, num_sms, err);
+  }
   if (op.N % 256 == 0 && !force_single_cta()) {
     p.num_m_tiles = ceil_div(op.M, 256);
     p.num_n_tiles = op.N / 256;
