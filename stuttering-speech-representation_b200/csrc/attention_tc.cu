@@ -37,18 +37,34 @@ namespace {
 constexpr int QT = 128;   // queries per item
 constexpr int KBLK = 64;  // keys per block
 constexpr int HD = 64;
-constexpr int KV_STAGES = 4;
 constexpr int Q_BYTES = 128 * 64 * 2;   // [128 x 64] bf16
 constexpr int KV_BYTES = 64 * 64 * 2;   // [64 x 64] bf16 (K or V of one block)
 constexpr int P_BYTES = 128 * 64 * 2;   // [128 q x 64 keys] bf16
 constexpr int SM_Q = 0;
-constexpr int SM_KV = Q_BYTES;                               // KV_STAGES x (K, V)
-constexpr int SM_P = SM_KV + KV_STAGES * 2 * KV_BYTES;       // 2 buffers
-constexpr int SM_BAR = SM_P + 2 * P_BYTES;
-constexpr int ATT_SMEM = SM_BAR + 256;
+constexpr int SM_KV = Q_BYTES;  // KV_STAGES x (K, V)
+constexpr int WIN = 96;         // bias window per softmax warp and key block: 64 keys + 31 rows of skew (+1 pad)
+// The gated-bias kernel trades one K/V stage for the per-warp relative-position windows (2 CTAs per SM either way).
+template <bool HAS_BIAS>
+struct Lay {
+  static constexpr int KV_STAGES = HAS_BIAS ? 3 : 4;
+  static constexpr int SM_P = SM_KV + KV_STAGES * 2 * KV_BYTES;  // 2 buffers
+  static constexpr int SM_BAR = SM_P + 2 * P_BYTES;
+  static constexpr int SM_WIN = SM_BAR + 256;
+  static constexpr int SM_LEN = SM_BAR + 192;  // 6 x [2] int inside the barrier block: prefetched clip lengths
+  static constexpr int SM_GATE = SM_WIN + (HAS_BIAS ? 4 * WIN * 4 : 0);  // [2][128] fp32: prefetched gates
+  static constexpr int SMEM = SM_GATE + (HAS_BIAS ? 2 * 128 * 4 : 0);
+  static_assert(2 * (SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+};
 constexpr int TMEM_COLS = 256;
 constexpr int TM_S = 0, TM_O = 128;  // S[2] at columns 0 / 64, O at columns 128..191 (allocation is a power of two)
 constexpr float LOG2E = 1.4426950408889634f;
+
+#ifdef SSR_ATT_TRACE
+__device__ long long g_att_trace[3][1024];
+#define TR(role, ctr) do { if (blockIdx.x == 0 && (ctr) < 1024) g_att_trace[role][(ctr)++] = clock64(); } while (0)
+#else
+#define TR(role, ctr) do { } while (0)
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -74,15 +90,60 @@ struct Item {
 
 // Items are ordered query-tile-major (all first tiles, then all second tiles, ...) so that the statically strided
 // persistent CTAs each see the same mix of full and partial tiles.
-__device__ __forceinline__ Item decode_item(const AttentionArgs& a, int idx) {
+// Decoding is split so that the clip-length load of item n+1 is issued one whole item before its first use
+// (predecode at the top of item n, finish_item at the top of item n+1): no role ever stalls on it.
+struct ItemPre {
+  int b, h, q0;
+};
+struct Step {
+  int dq, db, dh;  // gridDim.x in the mixed radix of the item index (host-computed: lives in the constant bank)
+};
+// Walks the item list of one CTA (idx = blockIdx.x + k * gridDim.x) without a division per item.
+struct Cursor {
+  int qt, b, h;  // current item: idx = (qt * B + b) * H + h
+  __device__ __forceinline__ void init(const AttentionArgs& a) {
+    const int bh = a.B * a.H;
+    qt = (int)blockIdx.x / bh;
+    const int rem = (int)blockIdx.x - qt * bh;
+    b = rem / a.H;
+    h = rem - b * a.H;
+  }
+  __device__ __forceinline__ void advance(const AttentionArgs& a, const Step& st) {
+    h += st.dh;
+    b += st.db;
+    qt += st.dq;
+    if (h >= a.H) {
+      h -= a.H;
+      ++b;
+    }
+    if (b >= a.B) {
+      b -= a.B;
+      ++qt;
+    }
+  }
+  // The clip length of the item goes global -> shared memory asynchronously (consumed one item later): a value
+  // prefetched into a register would be spilled by the compiler at once, i.e. waited for.
+  __device__ __forceinline__ ItemPre load(const AttentionArgs& a, int* len_slot, bool copy = true) const {
+    ItemPre p;
+    p.b = b;
+    p.h = h;
+    p.q0 = qt * QT;
+    if (copy)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(len_slot)), "l"(a.lens + b) : "memory");
+    return p;
+  }
+};
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ Item finish_item(const AttentionArgs& a, const ItemPre& p, int len_raw) {
   Item it;
-  const int bh = a.B * a.H;
-  const int qt = idx / bh;
-  const int rem = idx - qt * bh;
-  it.b = rem / a.H;
-  it.h = rem - it.b * a.H;
-  it.q0 = qt * QT;
-  it.len = min(__ldg(a.lens + it.b), a.slot);
+  it.b = p.b;
+  it.h = p.h;
+  it.q0 = p.q0;
+  it.len = min(len_raw, a.slot);
   it.valid = it.q0 < it.len;  // tiles past the clip's live frames are never consumed (engine.cu: slot layout)
   it.nkb = (it.len + KBLK - 1) / KBLK;
   return it;
@@ -102,8 +163,8 @@ __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, flo
   for (int k = 0; k < 32; k += 2) {
     float v0 = __uint_as_float(raw[k]), v1 = __uint_as_float(raw[k + 1]);
     if (HAS_BIAS) {
-      v0 = fmaf(gate, __ldg(rel + jg0 + k), v0);
-      v1 = fmaf(gate, __ldg(rel + jg0 + k + 1), v1);
+      v0 = fmaf(gate, rel[k], v0);  // rel: this row's view of the warp's shared-memory window (see WIN)
+      v1 = fmaf(gate, rel[k + 1], v1);
     }
     if (MASK) {
       if (jg0 + k >= len) v0 = -INFINITY;
@@ -134,7 +195,10 @@ __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, flo
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
-                    const AttentionArgs a, const int n_items) {
+                    const AttentionArgs a, const int n_items, const Step step) {
+  constexpr int KV_STAGES = Lay<HAS_BIAS>::KV_STAGES;
+  constexpr int SM_P = Lay<HAS_BIAS>::SM_P;
+  constexpr int SM_BAR = Lay<HAS_BIAS>::SM_BAR;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* q_full = bars + 0;
@@ -176,18 +240,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   if (threadIdx.x == 128) {
     // ============================ TMA producer ============================
     uint32_t n_item = 0, n = 0;
-    Item nxt = decode_item(a, blockIdx.x);
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-      const Item it = nxt;
-      if (idx + (int)gridDim.x < n_items) nxt = decode_item(a, idx + gridDim.x);  // prefetch the length load
+    int trc = 0; (void)trc;
+    Cursor cur;
+    cur.init(a);
+    int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + 8;  // [2] private to this thread
+    uint32_t lbuf = 0;
+    ItemPre nxt = cur.load(a, lsm);
+    cp_async_commit();
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
+      cp_async_wait_all();
+      const Item it = finish_item(a, nxt, lsm[lbuf]);
+      if (idx + (int)gridDim.x < n_items) {  // prefetch the next item's length
+        cur.advance(a, step);
+        nxt = cur.load(a, lsm + (lbuf ^ 1));
+        cp_async_commit();
+      }
       if (!it.valid) continue;
       const int row0 = it.b * a.slot;
       mbar_wait(q_empty, (n_item & 1) ^ 1);
+      TR(0, trc);
       mbar_arrive_expect_tx(q_full, Q_BYTES);
       tma_load_2d(smem + SM_Q, &tmq, q_full, it.h * HD, row0 + it.q0);
       for (int j = 0; j < it.nkb; ++j, ++n) {
         const int s = n % KV_STAGES;
         mbar_wait(&kv_empty[s], ((n / KV_STAGES) & 1) ^ 1);
+        TR(0, trc);
         mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
         tma_load_2d(smem + SM_KV + s * 2 * KV_BYTES, &tmkv, &kv_full[s], a.D + it.h * HD, row0 + j * KBLK);
         tma_load_2d(smem + SM_KV + s * 2 * KV_BYTES + KV_BYTES, &tmkv, &kv_full[s], 2 * a.D + it.h * HD,
@@ -202,12 +279,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     uint32_t n_item = 0, n = 0;
     bool have_prev = false, prev_first = false;
     int prev_n16 = 0;
+    int trc = 0; (void)trc;
     // PV of block n-1 is issued after S of block n and accumulates into O over the whole item (the softmax warps
     // rescale O in place on the rare occasion the softmax reference changes).
     auto issue_pv_prev = [&]() {
       const uint32_t pn = n - 1;
       const int ps = pn % KV_STAGES;
       mbar_wait(&bar_p[pn & 1], (pn >> 1) & 1);  // P_{n-1} is in shared memory, O is ready to take PV_{n-1}
+      TR(1, trc);
       tc_fence_after();
       const uint64_t dp = umma_desc_sw128(smem_u32(smem + SM_P + (pn & 1) * P_BYTES));
       const uint64_t dv = umma_desc_sw128_mn(smem_u32(smem + SM_KV + ps * 2 * KV_BYTES + KV_BYTES));
@@ -218,17 +297,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       umma_commit(&kv_empty[ps]);
       umma_commit(&bar_o[pn & 1]);
     };
-    Item nxt = decode_item(a, blockIdx.x);
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-      const Item it = nxt;
-      if (idx + (int)gridDim.x < n_items) nxt = decode_item(a, idx + gridDim.x);
+    Cursor cur;
+    cur.init(a);
+    int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + 10;  // [2] private to this thread
+    uint32_t lbuf = 0;
+    ItemPre nxt = cur.load(a, lsm);
+    cp_async_commit();
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
+      cp_async_wait_all();
+      const Item it = finish_item(a, nxt, lsm[lbuf]);
+      if (idx + (int)gridDim.x < n_items) {  // prefetch the next item's length
+        cur.advance(a, step);
+        nxt = cur.load(a, lsm + (lbuf ^ 1));
+        cp_async_commit();
+      }
       if (!it.valid) continue;
       mbar_wait(q_full, n_item & 1);
+      TR(1, trc);
       for (int j = 0; j < it.nkb; ++j) {
         const int s = n % KV_STAGES;
         const int nlive = min(KBLK, it.len - j * KBLK);
         const int n16 = (nlive + 15) >> 4;  // live keys in units of 16
         mbar_wait(&kv_full[s], (n / KV_STAGES) & 1);
+        TR(1, trc);
         tc_fence_after();
         const uint64_t dk = umma_desc_sw128(smem_u32(smem + SM_KV + s * 2 * KV_BYTES));
         const uint32_t idesc_s = umma_idesc_bf16(128, n16 * 16);
@@ -243,34 +334,63 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         prev_first = (j == 0);
         ++n;
       }
+      // The last PV of the item is not held back behind the next item's Q load (which can only be requested once
+      // this item's last S has retired): O reaches the softmax warps one TMA latency earlier.
+      issue_pv_prev();
+      have_prev = false;
       ++n_item;
     }
-    if (have_prev) issue_pv_prev();
   } else if (warp < 4) {
     // ============================ softmax / output warps ============================
     const uint32_t quad = warp;  // TMEM lane quadrant accessible to this warp
     const int il = quad * 32 + lane;
     const uint32_t lane_addr = (quad * 32u) << 16;
     uint32_t n = 0;
-    Item nxt = decode_item(a, blockIdx.x);
-    float gate_nxt = 0.f;
-    if (HAS_BIAS && nxt.q0 + il < a.slot)
-      gate_nxt = a.gate[((long long)nxt.b * a.slot + nxt.q0 + il) * a.H + nxt.h];
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
-      const Item it = nxt;
-      const float gate = gate_nxt;
+    int trc = 0; (void)trc;
+    Cursor cur;
+    cur.init(a);
+    int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + quad * 2;  // [2] per warp, copied by lane 0
+    ItemPre nxt = cur.load(a, lsm, lane == 0);
+    // The row's gate of the NEXT item travels global -> shared memory by cp.async (no register is live across the
+    // item, so nothing makes the warp wait for the load) and is read one item later; each thread reads its own word.
+    float* gsm = reinterpret_cast<float*>(smem + Lay<HAS_BIAS>::SM_GATE) + il;
+    uint32_t gbuf = 0;
+    auto prefetch_gate = [&](const ItemPre& p, uint32_t buf) {
+      if (HAS_BIAS && p.q0 + il < a.slot)
+        cp_async_f32(gsm + buf * 128, a.gate + ((long long)p.b * a.slot + p.q0 + il) * a.H + p.h);
+      cp_async_commit();  // closes the group that also holds the length copy
+    };
+    prefetch_gate(nxt, 0);
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, gbuf ^= 1) {
+      if (threadIdx.x == 0) TR(2, trc);
+      cp_async_wait_all();
+      __syncwarp();  // lane 0's length copy is visible to the warp
+      const Item it = finish_item(a, nxt, lsm[gbuf]);
+      float gate = 0.f;
+      if (HAS_BIAS) gate = gsm[gbuf * 128];
       // prefetch the next item's length and this row's gate: consumed one iteration later
       if (idx + (int)gridDim.x < n_items) {
-        nxt = decode_item(a, idx + gridDim.x);
-        if (HAS_BIAS && nxt.q0 + il < a.slot)
-          gate_nxt = a.gate[((long long)nxt.b * a.slot + nxt.q0 + il) * a.H + nxt.h];
+        cur.advance(a, step);
+        nxt = cur.load(a, lsm + (gbuf ^ 1), lane == 0);
+        prefetch_gate(nxt, gbuf ^ 1);
       }
       if (!it.valid) continue;
+      if (threadIdx.x == 0) TR(2, trc);
       const int row0 = it.b * a.slot;
-      const int i = it.q0 + il;                                // query index inside the clip
       const bool warp_live = it.q0 + (int)quad * 32 < it.len;   // at least one live query row in this warp
-      const float* rel = nullptr;
-      if (HAS_BIAS) rel = a.relbias + (long long)it.h * a.rel_stride + a.rel_center - i;  // rel[j] = table[h][j - i]
+      // Gated bias: row i needs table[h][j - i] for the 64 keys j of a block. The 32 rows of a warp together touch
+      // only 95 consecutive table entries per block, so the warp stages that window in shared memory (3 coalesced
+      // loads per lane, issued before the wait for S) and every row reads its 64 values at a lane-dependent skew:
+      // win[x] = table[h][64 j_blk + x - 31 - i_lane0]  =>  row (lane l), key k of the block: win[k + 31 - l].
+      // (Per-element global loads cost two L1 wavefronts each and made the bias blocks twice as long as plain ones.)
+      float* win = reinterpret_cast<float*>(smem + Lay<HAS_BIAS>::SM_WIN) + quad * WIN;
+      const float* rel = win + 31 - lane;
+      const float* table = nullptr;
+      int win_base = 0;
+      if (HAS_BIAS) {
+        table = a.relbias + (long long)it.h * a.rel_stride;
+        win_base = a.rel_center - 31 - (it.q0 + (int)quad * 32);
+      }
       {
         // ---------------- O accumulates in TMEM over the whole item ----------
         // Block 0 takes the exact row maximum as the softmax reference. Later blocks exponentiate against that
@@ -287,22 +407,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           const bool need_mask = (nlive & 31) != 0;
           const uint32_t ts = tmem + lane_addr + TM_S + (n & 1) * 64;
           uint8_t* prow = smem + SM_P + (n & 1) * P_BYTES + il * 128;
+          float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+          if (HAS_BIAS && warp_live) {
+            // entries outside the table belong to padded rows / masked keys only: clamp the index, never use the value
+            const int t0 = win_base + k0 + (int)lane, hi = a.rel_stride - 1;
+            w0 = __ldg(table + min(max(t0, 0), hi));
+            w1 = __ldg(table + min(max(t0 + 32, 0), hi));
+            w2 = __ldg(table + min(max(t0 + 64, 0), hi));
+          }
           mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
-          __syncwarp();
+          if (threadIdx.x == 0) TR(2, trc);
+          __syncwarp();  // also: every lane is done reading the previous block's window
           tc_fence_after();
           if (warp_live) {
+            if (HAS_BIAS) {
+              win[lane] = w0;
+              win[lane + 32] = w1;
+              win[lane + 64] = w2;
+              __syncwarp();
+            }
             float dummy = 0.f, l_blk = 0.f;
             uint32_t r0[32], r1[32];  // both chunks in flight before the single wait
             tmem_ld_32x32(ts, r0);
             if (nch == 2) tmem_ld_32x32(ts + 32, r1);
             tmem_wait_ld();
+            if (threadIdx.x == 0) TR(2, trc);
             float mu2;
             if (j == 0) {
               // exact row maximum of the first block; the biased / masked scores stay in the registers
               float m_blk = -INFINITY;
               if (nch == 2) {
                 chunk<HAS_BIAS, false, false, true, HAS_BIAS>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
-                chunk<HAS_BIAS, true, false, true, true>(r1, k0 + 32, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, true, false, true, true>(r1, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, l_blk, nullptr, 0);
               } else {
                 chunk<HAS_BIAS, true, false, true, true>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
               }
@@ -315,9 +451,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               if (nch == 2) {
                 chunk<HAS_BIAS, false, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
                 if (need_mask)
-                  chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel, mu2, dummy, l_blk, prow, 4);
+                  chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
                 else
-                  chunk<HAS_BIAS, false, true, false>(r1, k0 + 32, it.len, gate, rel, mu2, dummy, l_blk, prow, 4);
+                  chunk<HAS_BIAS, false, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
               } else {
                 if (need_mask)
                   chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
@@ -330,7 +466,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               // rare: raise the reference to this block's exact maximum (rows that do not need it keep theirs)
               float m_blk = -INFINITY, l_dummy = 0.f;
               chunk<HAS_BIAS, true, false>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_dummy, nullptr, 0);
-              if (nch == 2) chunk<HAS_BIAS, true, false>(r1, k0 + 32, it.len, gate, rel, 0.f, m_blk, l_dummy, nullptr, 0);
+              if (nch == 2) chunk<HAS_BIAS, true, false>(r1, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, l_dummy, nullptr, 0);
               const float m_new = unsafe ? fmaxf(m_ref, m_blk) : m_ref;
               const float alpha = (m_new == m_ref) ? 1.f : ex2_approx((m_ref - m_new) * LOG2E);
               m_ref = m_new;
@@ -356,17 +492,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               }
               l_blk = 0.f;
               chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
-              if (nch == 2) chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel, mu2, dummy, l_blk, prow, 4);
+              if (nch == 2) chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
             }
             l_run += l_blk;
+            if (threadIdx.x == 0) TR(2, trc);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            if (threadIdx.x == 0) TR(2, trc);
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[n & 1]);
+          if (threadIdx.x == 0) TR(2, trc);
         }
         // the one true round-trip wait per item: PV of the last block
         mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
+        if (threadIdx.x == 0) TR(2, trc);
         __syncwarp();
         tc_fence_after();
         if (warp_live) {
@@ -374,9 +514,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
           tmem_ld_32x32(tmem + lane_addr + TM_O, a0);
           tmem_ld_32x32(tmem + lane_addr + TM_O + 32, a1);
           tmem_wait_ld();
-          if (i < it.len) {
-            const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-            uint4* dst = reinterpret_cast<uint4*>(a.out + ((long long)row0 + i) * a.D + it.h * HD);
+          if (threadIdx.x == 0) TR(2, trc);
+          // A row of the output is 128 contiguous bytes: transpose through this warp's 32 rows of the P buffer the
+          // last PV has just finished reading (same XOR swizzle => conflict-free), so that each store instruction
+          // writes 4 whole rows instead of 32 scattered 16-byte pieces.
+          const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+          uint8_t* stage = smem + SM_P + ((n - 1) & 1) * P_BYTES + quad * 32 * 128;
+          {
+            uint8_t* mine = stage + lane * 128;
+            const uint32_t sw = lane & 7;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               uint32_t w[4];
@@ -388,10 +534,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                     __floats2bfloat162_rn(__uint_as_float(src[c]) * inv, __uint_as_float(src[c + 1]) * inv);
                 w[e] = *reinterpret_cast<uint32_t*>(&pk);
               }
-              dst[q] = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(mine + ((q ^ sw) * 16)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
+          __syncwarp();
+          if (threadIdx.x == 0) TR(2, trc);
+          {
+            const uint32_t rsub = lane >> 3, cch = lane & 7;
+            bf16* dst = a.out + ((long long)row0 + it.q0 + quad * 32) * a.D + it.h * HD + cch * 8;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const uint32_t r = t * 4 + rsub;
+              const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((cch ^ (r & 7)) * 16));
+              if (it.q0 + (int)(quad * 32 + r) < it.len) *reinterpret_cast<uint4*>(dst + (long long)r * a.D) = v;
+            }
+          }
+          __syncwarp();  // the staging rows are rewritten by this warp's next P tile
         }
+        if (threadIdx.x == 0) TR(2, trc);
         tc_fence_before();  // the TMEM reads above are ordered before the bar_p arrival that lets the next item's PV overwrite O
       }
     }
@@ -421,9 +581,9 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   static int num_sms = 148;
   if (!attr_set) {
     cudaError_t c1 =
-        cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::SMEM);
     cudaError_t c2 =
-        cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+        cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::SMEM);
     if (c1 != cudaSuccess || c2 != cudaSuccess) {
       err = std::string("cudaFuncSetAttribute(attention_tc_kernel): ") +
             cudaGetErrorString(c1 != cudaSuccess ? c1 : c2);
@@ -440,10 +600,14 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
     return -1;
   }
   const int grid = (int)(items < 2LL * num_sms ? items : 2LL * num_sms);
+  Step step;
+  step.dq = grid / (a.B * a.H);
+  step.db = (grid % (a.B * a.H)) / a.H;
+  step.dh = grid % a.H;
   if (a.gate != nullptr)
-    attention_tc_kernel<true><<<grid, 192, ATT_SMEM, st>>>(tmq, tmkv, a, (int)items);
+    attention_tc_kernel<true><<<grid, 192, Lay<true>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);
   else
-    attention_tc_kernel<false><<<grid, 192, ATT_SMEM, st>>>(tmq, tmkv, a, (int)items);
+    attention_tc_kernel<false><<<grid, 192, Lay<false>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("attention_tc launch: ") + cudaGetErrorString(ce);
@@ -453,3 +617,9 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
 }
 
 }  // namespace ssr
+
+#ifdef SSR_ATT_TRACE
+extern "C" int ssr_att_trace_fetch(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, ssr::g_att_trace, sizeof(long long) * 3 * 1024);
+}
+#endif
