@@ -19,9 +19,23 @@
 //                 (B=64, T=1500, H=20) 1.91 ms -> 1.29 ms per layer on peaked scores, 1.50 ms on flat scores (denser
 //                 P: the kernel is power-limited, 1.78 of 1.965 GHz under ncu); WavLM shape (B=256, T=149, H=16, gated
 //                 bias) 183 -> 168 us versus a per-block two-pass online softmax with a register accumulator.
-//   Two CTAs are co-resident per SM (112 KB smem, 256 TMEM columns each). Padding is not computed: the last key
+//   Two CTAs are co-resident per SM (<= 113 KB smem, 256 TMEM columns each). Padding is not computed: the last key
 //   block uses an MMA N / K extent rounded to 16 live keys, softmax touches only the 32-column chunks that hold live
 //   keys, and warps whose 32 query rows are all beyond the clip's length only keep the barrier protocol going.
+//
+//   What a per-warp-role timeline of one CTA (clock64 at every barrier; build with -DSSR_ATT_TRACE, tools/attn_trace.py)
+//   showed for the short WavLM items (3 key blocks), and what the kernel does about it:
+//     * the gated bias, fetched per element with __ldg, doubled the time of a block (two L1 wavefronts per load, all
+//       warps bursting at once) -> each warp stages the 95 table entries its 32 rows need per block in shared memory;
+//     * the last PV of an item was queued behind the next item's Q load (single Q buffer: that load can only be
+//       requested once this item's last S has retired, and takes ~2 us under load) -> it is issued at item end;
+//     * clip length and gate prefetched into registers were spilled at once, i.e. waited for -> they travel
+//       global -> shared by cp.async and are read one item later; the item walk needs no division;
+//     * output rows are transposed through the idle P buffer so that a store instruction writes 4 whole 128-byte rows.
+//   WavLM shape 167 -> 158 us per layer, Whisper shape 1318 -> 1262 us. What is left is a chain of fixed latencies per
+//   block (mbarrier wait, tcgen05.ld, proxy fence, arrive: ~900 of ~2400 cycles) that only more resident CTAs per SM
+//   could hide; 8 softmax warps per CTA (two per TMEM lane quadrant) and S running three blocks ahead of PV were both
+//   built and measured: slower / no change.
 //
 // Reference arithmetic: see attention.cu (same math; that mma.sync kernel is kept as a cross-check).
 #include "common.cuh"
