@@ -38,7 +38,6 @@ struct GemmParams {
   int M, N, K;
   int a_mode;  // 0: A[r, k] plain (tensor map {K, M});  1: positional conv, A[r, tap*64 + c] = X[r + tap, ntile*64 + c]
   int num_m_tiles, num_n_tiles, num_kb;
-  int m_tile0;  // first M tile of this launch (a GEMM may be split by rows into a body and a tail launch)
   EpiParams epi;
 };
 
@@ -65,8 +64,7 @@ struct PosConvOp {
 };
 
 // ---- launchers (each returns cudaError_t / sets message in err) ----
-int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err,
-                int* n_launched = nullptr);  // n_launched: kernels issued (a short last wave goes to a second launch)
+int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err);
 int launch_posconv(const PosConvOp& op, cudaStream_t stream, int num_sms, std::string& err);
 
 // 2-D bf16 tensor map: dim0 (contiguous) x dim1 rows of pitch `pitch_elems`; box = 64 x box_rows; 128-byte swizzle.

@@ -574,11 +574,9 @@ struct ProfScope {
 };
 
 int run_gemm(ssr_engine* e, const GemmOp& op, cudaStream_t st, const char* name = "gemm") {
+  e->launches += e->opt_simt ? (op.epi.pool_part ? 2 : 1) : 1;
   ProfScope ps(e, st, name, 2.0 * (double)op.M * (double)op.N * (double)op.K);
-  int nl = 1;
-  const int rc = launch_gemm(op, st, e->opt_simt != 0, e->num_sms, e->err, &nl);
-  e->launches += e->opt_simt ? (op.epi.pool_part ? 2 : 1) : nl;
-  return rc;
+  return launch_gemm(op, st, e->opt_simt != 0, e->num_sms, e->err);
 }
 
 int run_ln(ssr_engine* e, const LayerNormArgs& a, cudaStream_t st) {

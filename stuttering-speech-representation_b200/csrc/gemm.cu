@@ -302,9 +302,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_rel = tile / p.num_n_tiles;
-      const int n_tile = tile - m_rel * p.num_n_tiles;
-      const int m_tile = m_rel + p.m_tile0;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + Cfg::B_STAGE_BYTES);
@@ -355,9 +354,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t accph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_rel = tile / p.num_n_tiles;
-      const int n_tile = tile - m_rel * p.num_n_tiles;
-      const int m_tile = m_rel + p.m_tile0;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
       epilogue_tile<BN, 1>(p, stages[warp], tmem_base + acc * BN, warp, m_tile * BM + (int)warp * 32, n_tile * BN,
                            lane, 0, &tfull[acc], accph);
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -442,9 +440,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int s = 0;
     uint32_t ph = 0;
     for (int tile = cid; tile < total_tiles; tile += ncl) {
-      const int m_rel = tile / p.num_n_tiles;
-      const int n_tile = tile - m_rel * p.num_n_tiles;
-      const int m_tile = m_rel + p.m_tile0;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[s], ph ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (A_STAGE_BYTES + B2_STAGE_BYTES));
@@ -491,9 +488,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     int acc = 0;
     uint32_t accph = 0;
     for (int tile = cid; tile < total_tiles; tile += ncl) {
-      const int m_rel = tile / p.num_n_tiles;
-      const int n_tile = tile - m_rel * p.num_n_tiles;
-      const int m_tile = m_rel + p.m_tile0;
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
       epilogue_tile<BN, 2>(p, stages[warp], tmem_base + acc * BN, quad,
                            m_tile * 256 + (int)rank * 128 + (int)quad * 32, n_tile * BN, lane, split, &tfull[acc],
                            accph);
@@ -680,7 +676,7 @@ int launch_posconv(const PosConvOp& op, cudaStream_t stream, int num_sms, std::s
   pc.g.N = 1024;
   pc.g.K = 8192;
   pc.g.a_mode = 1;
-  pc.g.num_m_tiles = pc.g.num_n_tiles = pc.g.num_kb = pc.g.m_tile0 = 0;
+  pc.g.num_m_tiles = pc.g.num_n_tiles = pc.g.num_kb = 0;
   pc.g.epi = op.epi;
   if ((op.epi.ldo32 & 3) || (op.epi.ldo16 & 7) || (op.epi.ldr & 3)) {
     err = "posconv: output / residual leading dimensions must keep 16-byte row alignment";
@@ -906,23 +902,12 @@ static bool force_single_cta() {
   return v == 1;
 }
 
-static bool split_tail() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SSR_GEMM_TAIL_SPLIT");  // opt-in until measured on the GPU
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err, int* n_launched) {
-  if (n_launched != nullptr) *n_launched = 1;
+int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, std::string& err) {
   GemmParams p;
   p.M = op.M;
   p.N = op.N;
   p.K = op.K;
   p.a_mode = op.a_mode;
-  p.m_tile0 = 0;
   p.epi = op.epi;
   if (op.M <= 0 || op.N <= 0 || op.K <= 0) {
     err = "gemm: empty problem";
@@ -988,29 +973,8 @@ int launch_gemm(const GemmOp& op, cudaStream_t stream, bool simt, int num_sms, s
     return launch_tc<128>(op, p, stream, num_sms, err);
   }
   if (op.N % 256 == 0 && !force_single_cta()) {
-    const int mt = ceil_div(op.M, 256), nt = op.N / 256, clusters = num_sms / 2;
-    const int waves = (mt * nt) / clusters, rem = (mt * nt) % clusters;
-    // Wave quantisation: with few waves a short last one is expensive (FFN2 / out-proj of WavLM-Large at B = 256:
-    // 600 pair tiles on 74 SM pairs = 8 full waves + 8 tiles, i.e. a ninth wave at 11 % occupancy). The rows of that
-    // last wave go to a second launch with small single-CTA tiles that spreads them over the whole GPU.
-    const int body_mt = (waves * clusters) / nt;
-    if (split_tail() && waves >= 1 && waves <= 12 && rem > 0 && rem * 4 <= clusters && body_mt >= 1 && body_mt < mt) {
-      p.num_m_tiles = body_mt;
-      p.num_n_tiles = nt;
-      if (launch_tc2(op, p, stream, num_sms, err)) return -1;
-      if (n_launched != nullptr) *n_launched = 2;
-      GemmParams t = p;
-      t.m_tile0 = body_mt * 2;  // in 128-row tiles
-      t.num_m_tiles = ceil_div(op.M, BM) - t.m_tile0;
-      if ((long long)t.num_m_tiles * (op.N / 64) <= 2LL * num_sms) {
-        t.num_n_tiles = op.N / 64;
-        return launch_tc<64>(op, t, stream, num_sms, err);
-      }
-      t.num_n_tiles = op.N / 128;
-      return launch_tc<128>(op, t, stream, num_sms, err);
-    }
-    p.num_m_tiles = mt;
-    p.num_n_tiles = nt;
+    p.num_m_tiles = ceil_div(op.M, 256);
+    p.num_n_tiles = op.N / 256;
     return launch_tc2(op, p, stream, num_sms, err);
   }
   if (op.N % 256 == 0) {

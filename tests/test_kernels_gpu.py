@@ -122,52 +122,6 @@ def test_gemm_fused_pool(slot, lens, simt):
         assert (got - want).abs().max().item() < 2e-3, (b, (got - want).abs().max().item())
 
 
-def test_gemm_tail_split_rows():
-    """8 full waves of 256 x 256 pair tiles + a short ninth one: the last rows go to a second launch with small tiles
-    (launch_gemm); every row must come out of exactly one of the two launches, epilogue included."""
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    M, N, K = (sms * 2 + 2) * 256, 1024, 192      # WavLM-Large FFN2 / out-proj row count at B = 256 on 148 SMs
-    g = torch.Generator(device="cuda").manual_seed(17)
-    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
-    W = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
-    bias = torch.randn(N, device="cuda", generator=g)
-    resid = torch.randn(M, N, device="cuda", generator=g)
-    o32, o16 = gemm(A, K, M, W, M, N, K, bias=bias, act=1, resid=resid, want_bf16=True)
-    ref = ref_gemm(A, W, bias, 1, resid)
-    assert not torch.isnan(o32).any()
-    assert (o32 - ref).abs().max().item() < 5e-3
-    assert (o16.float() - ref).abs().max().item() < 5e-2
-
-
-def test_gemm_tail_split_fused_pool():
-    """Same split with the per-clip time pooling fused into the epilogue: the 32-row partial sums of the tail rows are
-    written by the second launch, ragged lengths included."""
-    lib = _lib()
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    slot = 150
-    B = (sms * 2 + 2) * 256 // slot  # 256 clips on 148 SMs
-    M, N, K = B * slot, 1024, 128
-    g = torch.Generator(device="cuda").manual_seed(19)
-    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
-    W = (torch.randn(N, K, device="cuda", generator=g) * 0.1).bfloat16()
-    resid = torch.randn(M, N, device="cuda", generator=g)
-    lens = torch.randint(1, slot + 1, (B,), generator=torch.Generator().manual_seed(2)).to(torch.int32)
-    lens[-3:] = torch.tensor([149, 150, 37], dtype=torch.int32)  # the clips inside the tail rows
-    lens_t = lens.cuda()
-    out = torch.zeros(M, N, device="cuda")
-    part = torch.full(((M + 31) // 32 * 2 * N,), float("nan"), device="cuda")
-    pooled = torch.full((B, N), float("nan"), device="cuda")
-    e = _err()
-    rc = lib.ssr_gemm_bf16_pool(0, A.data_ptr(), K, W.data_ptr(), M, N, K, None, 0, resid.data_ptr(), out.data_ptr(),
-                                slot, lens_t.data_ptr(), B, part.data_ptr(), pooled.data_ptr(), N, 0, None, e, 512)
-    torch.cuda.synchronize()
-    assert rc == 0, e.value.decode()
-    ref = ref_gemm(A, W, None, 0, resid).view(B, slot, N)
-    mask = (torch.arange(slot, device="cuda")[None, :] < lens_t[:, None]).float()
-    want = (ref * mask[:, :, None]).sum(1) / lens_t[:, None].float()
-    assert (pooled - want).abs().max().item() < 2e-3
-
-
 @pytest.mark.parametrize("D", [512, 768, 1024, 1280])
 @pytest.mark.parametrize("bf16_in,gelu", [(False, 0), (True, 1)])
 def test_layernorm(D, bf16_in, gelu):
