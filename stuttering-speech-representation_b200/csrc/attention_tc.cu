@@ -3,7 +3,7 @@
 // Persistent, warp-specialised kernel; a work item is one (clip, head, 128-query tile); each item loops over
 // 64-key blocks. Everything is double buffered so that the softmax warps never wait for a tensor-core round trip
 // in steady state:
-//     warp 4      TMA producer: Q per item, K_j / V_j tiles through a 4-stage ring that runs ahead across items,
+//     warp 4      TMA producer: Q per item, K_j / V_j tiles through a 4-stage ring (3 with the gated bias) that runs ahead,
 //                 all straight out of the fused qkv activation matrix (no head split / transpose pass)
 //     warp 5      single-thread tcgen05.mma issuer. S_{n+1} = Q K^T is issued BEFORE PV_n, so the next block's scores
 //                 are computed while the softmax warps work on the current one:
@@ -245,6 +245,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   if (warp == 5) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
+  }
+  if (HAS_BIAS && threadIdx.x < 128) {
+    // rows beyond the clip slot never get a gate copied: they must read a finite value, not stale shared memory
+    float* g0 = reinterpret_cast<float*>(smem + Lay<HAS_BIAS>::SM_GATE);
+    g0[threadIdx.x] = 0.f;
+    g0[128 + threadIdx.x] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
