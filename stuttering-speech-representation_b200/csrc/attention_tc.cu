@@ -104,8 +104,8 @@ struct Item {
 
 // Items are ordered query-tile-major (all first tiles, then all second tiles, ...) so that the statically strided
 // persistent CTAs each see the same mix of full and partial tiles.
-// Decoding is split so that the clip-length load of item n+1 is issued one whole item before its first use
-// (predecode at the top of item n, finish_item at the top of item n+1): no role ever stalls on it.
+// Decoding is split so that the clip-length fetch of item n+1 is issued one whole item before its first use
+// (Cursor::load at the top of item n, finish_item at the top of item n+1): no role ever stalls on it.
 struct ItemPre {
   int b, h, q0;
 };
