@@ -14,10 +14,16 @@
  *     (text via ssr_last_error). The Python shim turns any non-zero return into "log + return None",
  *     which is the reference's error convention (WavLM_embeddings.py:329-341).
  *   - the caller owns every buffer; the engine owns packed weights and its workspace arena.
- *   - *_dev entry points are asynchronous on the given CUDA stream (a cudaStream_t passed as void*; NULL =
- *     legacy default stream) and never synchronise; *_host entry points copy in, run, copy out and
- *     synchronise the stream before returning.
- *   - one engine per (process, device); not thread-safe by design (the reference is single-threaded).
+ *   - the device-buffer entry points (ssr_wavlm_pooled, ssr_whisper_enc_pooled, ssr_whisper_full, ssr_logmel) are
+ *     asynchronous on the given CUDA stream (a cudaStream_t passed as void*; NULL = legacy default stream). They
+ *     do not synchronise in steady state: the host n_samples array is copied into a pinned ring owned by the engine
+ *     before the call returns (the caller may reuse it at once) and travels to the device from there. The one
+ *     exception is workspace growth: the first call with a larger batch / longer clips than any before reallocates
+ *     (cudaFree / cudaMalloc synchronise). *_host entry points copy in, run, copy out and synchronise the stream
+ *     before returning.
+ *   - one engine per (process, device), one host thread at a time (the reference is single-threaded). Calls on
+ *     DIFFERENT streams are ordered by the engine (its workspace is shared): each forward waits, on the device,
+ *     for the previous forward of the same engine whichever stream that ran on.
  *   - pooled output layout: float32 [B, L+1, D], layer-major per clip, so pooled[b, i, :] equals
  *     torch.mean(hidden_states[i], dim=1) of the reference for clip b, for every i in 0..L
  *     (hidden_states order: HF modeling_wavlm.py:412-439,488-516; modeling_whisper.py:550-553 + output_capturing).
@@ -104,6 +110,10 @@ int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_
 /* Number of frames the model produces for a clip of n samples (WavLM conv arithmetic, HF modeling_wavlm.py:647-653;
  * Whisper: always 1500). */
 int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples);
+/* WavLM relative-position bucket of rel = key_index - query_index (the one piece of integer arithmetic on the path:
+ * HF WavLMAttention._relative_positions_bucket, modeling_wavlm.py:252-271, num_buckets 320, max_distance 800).
+ * Host function, needs no device; the engine builds its [H, 2R-1] relative-bias table (debug tap "relbias") from it. */
+int32_t ssr_wavlm_rel_bucket(int32_t rel);
 /* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t ssr_launch_count(const ssr_engine* e);
 /* With option "profile" = 1: synchronises, then returns a JSON object

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <string>
@@ -43,8 +44,8 @@ inline uint16_t f2bf(float f) {
 }
 
 // Bumped by every workspace (re)allocation: cached device state that bakes pointers in (uploaded lengths, captured
-// CUDA graphs) is only valid for the epoch it was made in.
-uint64_t g_arena_epoch = 1;
+// CUDA graphs) is only valid for the epoch it was made in. Atomic: engines of different host threads share it.
+std::atomic<uint64_t> g_arena_epoch{1};
 
 struct Buf {
   void* p = nullptr;
@@ -157,6 +158,18 @@ struct ssr_engine {
   const void *up_ptr_n = nullptr, *up_ptr_l = nullptr;
   cudaStream_t up_stream = nullptr;
   bool capturing = false;
+  // Lengths travel host -> device through a small pinned ring owned by the engine: a cudaMemcpyAsync from pageable
+  // memory (the caller's n_samples, a stack vector) would be staged by the runtime and synchronise the stream.
+  static constexpr int kLenRing = 8;
+  int* len_ring = nullptr;        // pinned, kLenRing slots of 2 * len_ring_cap ints (n_samples | frame counts)
+  int len_ring_cap = 0;
+  int len_ring_next = 0;
+  cudaEvent_t len_ring_done[kLenRing] = {};
+  // One workspace serves every entry point: a forward on stream B must not start while a forward on stream A is
+  // still using it. Every entry point makes its stream wait for the previous forward's completion event.
+  cudaEvent_t last_done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_valid = false;
   // Small host-entry batches are launch-latency bound (about 210 kernels per WavLM-Large forward): the second
   // identical call (same model path, batch, pitch and lengths — the reference's per-clip loop over equal-length
   // clips) is captured into a CUDA graph and replayed from then on.
@@ -181,6 +194,10 @@ struct ssr_engine {
 
   ~ssr_engine() {
     drop_graph();
+    for (cudaEvent_t ev : len_ring_done)
+      if (ev) cudaEventDestroy(ev);
+    if (len_ring) cudaFreeHost(len_ring);
+    if (last_done) cudaEventDestroy(last_done);
     if (host_fence) cudaEventDestroy(host_fence);
     if (host_stream) cudaStreamDestroy(host_stream);
     for (void* p : owned) cudaFree(p);
@@ -290,6 +307,8 @@ int rel_bucket(int rel) {
   return bucket + (int)large;
 }
 
+void reg_dbg(ssr_engine* e, const char* name, const void* p, int dtype, int64_t d0, int64_t d1, int64_t d2, int64_t d3);
+
 int build_relbias(ssr_engine* e, int R, cudaStream_t st, std::string& err) {
   if (R <= e->rel_R) return 0;
   int newR = 256;
@@ -304,6 +323,7 @@ int build_relbias(ssr_engine* e, int R, cudaStream_t st, std::string& err) {
   CK(cudaMemcpyAsync(e->relbias.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
   e->rel_R = newR;
+  reg_dbg(e, "relbias", e->relbias.p, 0, H, W, 1, 1);
   return 0;
 }
 
@@ -847,18 +867,57 @@ int upload_lengths(ssr_engine* e, const int32_t* n_samples, int B, const std::ve
       (int)e->up_nsamp.size() == B && e->up_lens == lens &&
       memcmp(e->up_nsamp.data(), n_samples, sizeof(int) * B) == 0)
     return 0;
-  if (e->capturing) {  // a host-to-device copy from a stack vector must not end up inside a replayed graph
+  if (e->capturing) {  // a captured graph contains no length upload: it relies on what the buffers hold
     err = "length upload needed during graph capture";
     return -1;
   }
+  // The device length buffers are about to change: a captured graph was recorded against their old contents.
+  e->drop_graph();
   e->up_nsamp.clear();  // stays empty if a copy below fails
-  CK(cudaMemcpyAsync(e->nsamp_dev.p, n_samples, sizeof(int) * B, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(e->lens_dev.p, lens.data(), sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  if (B > e->len_ring_cap) {
+    // grow the pinned ring (rare: only when the batch size exceeds every earlier one); all slots must be idle
+    for (cudaEvent_t ev : e->len_ring_done)
+      if (ev) CK(cudaEventSynchronize(ev));
+    if (e->len_ring) CK(cudaFreeHost(e->len_ring));
+    e->len_ring = nullptr;
+    e->len_ring_cap = 0;
+    int cap = 64;
+    while (cap < B) cap *= 2;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&e->len_ring), sizeof(int) * 2 * (size_t)cap * ssr_engine::kLenRing));
+    e->len_ring_cap = cap;
+    for (cudaEvent_t& ev : e->len_ring_done)
+      if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  const int k = e->len_ring_next;
+  e->len_ring_next = (k + 1) % ssr_engine::kLenRing;
+  CK(cudaEventSynchronize(e->len_ring_done[k]));  // the copy issued kLenRing uploads ago; returns at once if unused
+  int* slot_n = e->len_ring + (size_t)k * 2 * e->len_ring_cap;
+  int* slot_l = slot_n + e->len_ring_cap;
+  memcpy(slot_n, n_samples, sizeof(int) * B);
+  memcpy(slot_l, lens.data(), sizeof(int) * B);
+  CK(cudaMemcpyAsync(e->nsamp_dev.p, slot_n, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(e->lens_dev.p, slot_l, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(e->len_ring_done[k], st));
   e->up_nsamp.assign(n_samples, n_samples + B);
   e->up_lens = lens;
   e->up_ptr_n = e->nsamp_dev.p;
   e->up_ptr_l = e->lens_dev.p;
   e->up_stream = st;
+  return 0;
+}
+
+// Entry / exit of every forward: cross-stream ordering on the shared workspace (see ssr_engine::last_done).
+int forward_enter(ssr_engine* e, cudaStream_t st) {
+  std::string& err = e->err;
+  if (e->last_valid && e->last_stream != st) CK(cudaStreamWaitEvent(st, e->last_done, 0));
+  return 0;
+}
+int forward_leave(ssr_engine* e, cudaStream_t st) {
+  std::string& err = e->err;
+  if (!e->last_done) CK(cudaEventCreateWithFlags(&e->last_done, cudaEventDisableTiming));
+  CK(cudaEventRecord(e->last_done, st));
+  e->last_stream = st;
+  e->last_valid = true;
   return 0;
 }
 
@@ -1432,7 +1491,11 @@ int ssr_wavlm_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_ld, co
     return -1;
   }
   cudaSetDevice(e->device);
-  return wavlm_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, as_stream(cuda_stream));
+  cudaStream_t st = as_stream(cuda_stream);
+  if (forward_enter(e, st)) return -1;
+  const int rc = wavlm_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, st);
+  if (forward_leave(e, st)) return -1;
+  return rc;
 }
 
 int ssr_whisper_enc_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples,
@@ -1447,7 +1510,11 @@ int ssr_whisper_enc_pooled(ssr_engine* e, const float* audio_dev, int64_t audio_
     return -1;
   }
   cudaSetDevice(e->device);
-  return whisper_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, as_stream(cuda_stream));
+  cudaStream_t st = as_stream(cuda_stream);
+  if (forward_enter(e, st)) return -1;
+  const int rc = whisper_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, st);
+  if (forward_leave(e, st)) return -1;
+  return rc;
 }
 
 int ssr_logmel(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const int32_t* n_samples, int32_t B,
@@ -1463,7 +1530,11 @@ int ssr_logmel(ssr_engine* e, const float* audio_dev, int64_t audio_ld, const in
   }
   cudaSetDevice(e->device);
   if (B == 0) return 0;
-  return whisper_logmel(e, audio_dev, audio_ld, n_samples, B, mel_dev, false, as_stream(cuda_stream));
+  cudaStream_t st = as_stream(cuda_stream);
+  if (forward_enter(e, st)) return -1;
+  const int rc = whisper_logmel(e, audio_dev, audio_ld, n_samples, B, mel_dev, false, st);
+  if (forward_leave(e, st)) return -1;
+  return rc;
 }
 
 // The host entry points run on a private stream (the legacy default stream cannot be captured into a graph). It is
@@ -1552,6 +1623,7 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
   cudaSetDevice(e->device);
   cudaStream_t st = nullptr;
   if (host_entry_stream(e, &st)) return -1;
+  if (forward_enter(e, st)) return -1;
   const size_t in_bytes = (size_t)B * audio_ld * 4;
   const size_t out_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
   if (e->audio_stage.ensure(in_bytes, st, err)) return -1;
@@ -1561,6 +1633,7 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
                            e->pooled_stage.as<float>(), nullptr, st);
   if (rc) return rc;
   CK(cudaMemcpyAsync(pooled_host, e->pooled_stage.p, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (forward_leave(e, st)) return -1;
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1599,7 +1672,11 @@ int ssr_whisper_full(ssr_engine* e, const float* audio_dev, int64_t audio_ld, co
     return -1;
   }
   cudaSetDevice(e->device);
-  return whisper_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, as_stream(cuda_stream), dec_dev);
+  cudaStream_t st = as_stream(cuda_stream);
+  if (forward_enter(e, st)) return -1;
+  const int rc = whisper_forward(e, audio_dev, audio_ld, n_samples, B, pooled_dev, st, dec_dev);
+  if (forward_leave(e, st)) return -1;
+  return rc;
 }
 
 int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_ld, const int32_t* n_samples,
@@ -1618,6 +1695,7 @@ int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_
   cudaSetDevice(e->device);
   cudaStream_t st = nullptr;
   if (host_entry_stream(e, &st)) return -1;
+  if (forward_enter(e, st)) return -1;
   const size_t in_bytes = (size_t)B * audio_ld * 4;
   const size_t enc_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
   const size_t dec_bytes = (size_t)B * (e->dec_L + 1) * e->d.hidden * 4;
@@ -1633,6 +1711,7 @@ int ssr_whisper_full_host(ssr_engine* e, const float* audio_host, int64_t audio_
   if (forward_graphed(e, 1, e->audio_stage.as<float>(), audio_ld, n_samples, B, enc_dev, dec_dev, st)) return -1;
   CK(cudaMemcpyAsync(pooled_host, enc_dev, enc_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(dec_host, dec_dev, dec_bytes, cudaMemcpyDeviceToHost, st));
+  if (forward_leave(e, st)) return -1;
   CK(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1643,6 +1722,8 @@ int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples) {
 }
 
 int64_t ssr_launch_count(const ssr_engine* e) { return e ? e->launches : -1; }
+
+int32_t ssr_wavlm_rel_bucket(int32_t rel) { return rel_bucket(rel); }
 
 int ssr_gemm_bf16(int32_t cuda_device, const void* A, int64_t lda, int64_t a_rows, const void* W, int32_t M,
                   int32_t N, int32_t K, const float* bias, int32_t act, const float* resid, float* out_f32,

@@ -132,6 +132,11 @@ def whisper_full_config(name: str):
         return WhisperConfig(d_model=768, encoder_layers=3, encoder_attention_heads=12, encoder_ffn_dim=3072,
                              decoder_layers=4, decoder_attention_heads=12, decoder_ffn_dim=3072, num_mel_bins=80,
                              vocab_size=51865)
+    if name == "wide_full":  # Whisper-large WIDTH (d=1280, 20 heads, ffn 5120) at 2 + 2 layers: reaches every
+        # kernel instantiation the `large` branch of REF/whisper_embeddings_large.py:442-455 uses
+        return WhisperConfig(d_model=1280, encoder_layers=2, encoder_attention_heads=20, encoder_ffn_dim=5120,
+                             decoder_layers=2, decoder_attention_heads=20, decoder_ffn_dim=5120, num_mel_bins=80,
+                             vocab_size=51865)
     raise KeyError(name)
 
 

@@ -200,3 +200,29 @@ def test_pipeline_on_disk_contract_and_resume(tmp_path):
     res2 = pipeline.extract_split(rows, pooled_fn, [2, 1], out, "train", clips.get, batch_size=4, resume=True)
     assert calls == [1] and len(res2) == 7
     assert pipeline.find_latest_checkpoint(out, "train") == 2
+
+
+def test_product_bucket_function_bit_exact_vs_hf():
+    """A6 is the one piece of integer work on the path: the PRODUCT's own C function (csrc/engine.cu rel_bucket,
+    exported as ssr_wavlm_rel_bucket; it fills the device relative-bias table) against HF
+    WavLMAttention._relative_positions_bucket (modeling_wavlm.py:252-271) for every rel in [-4000, 4000], and
+    against the known answers of SURVEY.md 8(c). Bit-exact, no tolerance."""
+    import hashlib
+
+    import torch
+    from transformers.models.wavlm.modeling_wavlm import WavLMAttention
+
+    from ssr_b200 import _lib
+
+    lib = _lib.load()
+    att = WavLMAttention(embed_dim=64, num_heads=1)
+    rel = torch.arange(-4000, 4001)
+    want = att._relative_positions_bucket(rel).numpy()
+    got = np.array([lib.ssr_wavlm_rel_bucket(int(r)) for r in rel.tolist()], dtype=want.dtype)
+    np.testing.assert_array_equal(got, want)
+    kat = {1: 161, -1: 1, 79: 239, -79: 79, 80: 240, 81: 240, -81: 80, 100: 247, -100: 87, 120: 254, -120: 94,
+           148: 261, -148: 101, 0: 0}
+    for r, b in kat.items():
+        assert lib.ssr_wavlm_rel_bucket(r) == b, r
+    lut = np.array([lib.ssr_wavlm_rel_bucket(r) for r in range(-148, 149)], dtype=np.int16)
+    assert hashlib.sha256(lut.tobytes()).hexdigest().startswith("67859a4d9be1a425")

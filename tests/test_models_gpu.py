@@ -267,7 +267,9 @@ def test_whisper_vs_reference_golden(name):
     if name == "tiny":
         clips = synth.mixed_clips() + synth.noise_clips(1, 480000, seed=5)
     else:
-        clips = [synth.noise_clips(1, 48000, seed=1234)[0], synth.tonal_clip(48000)]
+        # the third clip fills the whole 30 s window (BASELINE configs[2], second half)
+        clips = [synth.noise_clips(1, 48000, seed=1234)[0], synth.tonal_clip(48000),
+                 synth.noise_clips(1, 480000, seed=5)[0]]
     got = eng.pooled(clips)
     check_pooled(got, g["pooled"], f"whisper {name}")
 
@@ -446,6 +448,71 @@ def test_graph_replay_of_repeated_small_batches():
     np.testing.assert_array_equal(eng.pooled([a[5]]), want[5])
     np.testing.assert_array_equal(eng.pooled([a[6]]), want[6])
     np.testing.assert_array_equal(eng.pooled([a[7]]), want[7])
+
+
+def test_graph_replay_survives_interleaved_length_uploads():
+    """A replayed graph contains no length upload, so anything that rewrites the device length buffers between two
+    replays (a ragged batch above the graph limit, a device-entry call, a call on another stream) must invalidate
+    it. Sequence from the round-1 review: grow the arena, capture on clip A, run 24 clips of OTHER lengths whose first
+    length differs from A's, then call with A' (A's length) again."""
+    import torch
+
+    from ssr_b200 import synth
+
+    _, _, eng = wavlm("tiny_stable")
+    eng.set_option("graphs", 0)
+    a = [synth.clip_by_index(100 + i, 16000) for i in range(4)]
+    ragged = [synth.clip_by_index(200 + i, 9000 + 400 * i) for i in range(24)]
+    want = [eng.pooled([c]) for c in a]
+    want_ragged = eng.pooled(ragged)
+    eng.set_option("graphs", 1)
+    eng.pooled(ragged)                                           # arena fully grown
+    np.testing.assert_array_equal(eng.pooled([a[0]]), want[0])   # eager
+    np.testing.assert_array_equal(eng.pooled([a[1]]), want[1])   # capture
+    np.testing.assert_array_equal(eng.pooled([a[2]]), want[2])   # replay
+    np.testing.assert_array_equal(eng.pooled(ragged), want_ragged)   # B > 16: rewrites nsamp_dev / lens_dev
+    np.testing.assert_array_equal(eng.pooled([a[3]]), want[3])   # must NOT replay against clip 0 of `ragged`
+    np.testing.assert_array_equal(eng.pooled([a[0]]), want[0])
+    np.testing.assert_array_equal(eng.pooled([a[1]]), want[1])   # replaying again
+    # a device-entry call on a side stream in between (what augment_and_extract / pooled_stream do)
+    side = torch.cuda.Stream()
+    dev = torch.from_numpy(np.stack([ragged[5][:9000], ragged[6][:9000]])).cuda()
+    with torch.cuda.stream(side):
+        side.wait_stream(torch.cuda.current_stream())
+        got_dev = eng.pooled_device(dev, [9000, 8000], stream=side)
+    one = eng.pooled([a[2]])                                     # issued while the side-stream forward may be in flight
+    side.synchronize()
+    np.testing.assert_array_equal(one, want[2])
+    eng.set_option("graphs", 0)
+    np.testing.assert_array_equal(got_dev.cpu().numpy(), eng.pooled([ragged[5][:9000], ragged[6][:8000]]))
+    eng.set_option("graphs", 1)
+
+
+def test_device_relbias_table_is_the_hf_bucket_gather():
+    """The device relative-bias table (debug tap "relbias", [H, 2R-1]) must equal rel_attn_embed[bucket(rel), h] with
+    HF's bucket function for every rel it covers — bit-exact (integer index work + a gather)."""
+    import torch
+    from transformers.models.wavlm.modeling_wavlm import WavLMAttention
+
+    from ssr_b200 import synth
+
+    model, _, eng = wavlm("tiny_stable")
+    eng.pooled([synth.clip_by_index(0, 16000)])
+    tab = eng.debug_fetch("relbias")
+    H, W = tab.shape
+    R = (W + 1) // 2
+    assert H == model.config.num_attention_heads and R >= 256
+    emb = model.encoder.layers[0].attention.rel_attn_embed.weight.detach().numpy()   # [320, H]
+    att = WavLMAttention(embed_dim=64, num_heads=1)
+    rel = torch.arange(-(R - 1), R)
+    bucket = att._relative_positions_bucket(rel).numpy()
+    np.testing.assert_array_equal(tab, emb[bucket].T)
+    # and the implied bucket index, recovered from the table, is HF's
+    for r in (-2047, -800, -81, -80, -1, 0, 1, 79, 80, 81, 799, 800, 2047):
+        if abs(r) <= R - 1:
+            col = tab[:, r + R - 1]
+            hit = np.nonzero((emb == col[None, :]).all(1))[0]
+            assert int(bucket[r + R - 1]) in hit.tolist(), r
 
 
 def test_single_row_views_with_degenerate_stride():

@@ -30,7 +30,9 @@ def check(got, ref, what, cos_min=0.9999, rel_max=1e-2):
     assert np.isfinite(got).all() and cos.min() >= cos_min and rel.max() <= rel_max, what
 
 
-@pytest.mark.parametrize("name", ["tiny_full", "mid_full"])
+# wide_full has Whisper-large's width (d=1280, 20 heads, ffn 5120): dec_xattn_kernel<5>, dec_gemv and the token
+# GEMMs at D=1280 / F=5120 — the instantiations REF/whisper_embeddings_large.py:442-455 (`large`) needs
+@pytest.mark.parametrize("name", ["tiny_full", "mid_full", "wide_full"])
 def test_encoder_and_decoder_vs_reference_golden(name):
     from ssr_b200 import synth
 
@@ -93,3 +95,19 @@ def test_dropin_returns_decoder_layers(tmp_path):
     assert list(out2) == names[:2]
     for k in out2:
         np.testing.assert_allclose(out2[k], out[k], rtol=0, atol=2e-5 * max(1.0, np.abs(out[k]).max()))
+
+
+def test_decoder_large_width_batched_token_gemms():
+    """B > 16 sends the token-level Linear layers through the tensor-core GEMM instead of the GEMV kernel; both must
+    agree with each other at Whisper-large width (the first four clips are the golden's)."""
+    from ssr_b200 import synth
+
+    model, fe, eng = full("wide_full")
+    g = np.load(os.path.join(GOLD, "whisper_wide_full.npz"))
+    clips = synth.mixed_clips()[:4]
+    many = clips + [synth.clip_by_index(i, 30000 + 1000 * i) for i in range(16)]
+    enc, dec = eng.pooled_with_decoder(many)
+    check(enc[:4], g["encoder"], "wide_full encoder pooled (B=20)")
+    check(dec[:4], g["decoder"], "wide_full decoder states (B=20, GEMM path)")
+    _, dec_small = eng.pooled_with_decoder(clips)
+    check(dec_small, dec[:4], "GEMV vs GEMM token path", cos_min=0.99999, rel_max=8e-3)

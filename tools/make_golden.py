@@ -115,11 +115,12 @@ def main():
         pooled, ck = run_whisper(ref_whisper, "tiny", clips)
         np.savez_compressed(os.path.join(OUT, "whisper_tiny.npz"), pooled=pooled, checksum=ck)
     if want("whisper_large"):
-        clips = [synth.noise_clips(1, 48000, seed=1234)[0], synth.tonal_clip(48000)]
+        clips = [synth.noise_clips(1, 48000, seed=1234)[0], synth.tonal_clip(48000),
+                 synth.noise_clips(1, 480000, seed=5)[0]]  # the third one fills the whole 30 s window
         pooled, ck = run_whisper(ref_whisper, "large", clips)
         np.savez_compressed(os.path.join(OUT, "whisper_large.npz"), pooled=pooled, checksum=ck)
     # full Whisper models (encoder + decoder): every encoder_layer_* AND decoder_layer_* output of the reference
-    for full in ("tiny_full", "mid_full"):
+    for full in ("tiny_full", "mid_full", "wide_full"):
         if want("whisper_" + full):
             model, fe = synth.build_whisper_model(full, 0)
             ne, nd = model.config.encoder_layers + 1, model.config.decoder_layers + 1
