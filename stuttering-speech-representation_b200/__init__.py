@@ -11,12 +11,13 @@ from .extract import (  # noqa: F401
     extract_wavlm_embeddings,
     extract_whisper_embeddings_fixed,
     get_engine,
+    invalidate_engine,
     pooled_to_layer_dict,
 )
 
 __all__ = [
     "SsrError", "WavLMEngine", "WhisperEncoderEngine", "iter_batches", "shard_range",
     "extract_wavlm_embeddings", "extract_embeddings_from_audio_wavlm", "extract_whisper_embeddings_fixed",
-    "extract_embeddings_from_audio_whisper", "get_engine", "pooled_to_layer_dict", "augment_audio",
+    "extract_embeddings_from_audio_whisper", "get_engine", "invalidate_engine", "pooled_to_layer_dict", "augment_audio",
     "augment_and_extract",
 ]

@@ -35,22 +35,53 @@ logger = logging.getLogger("ssr_b200")
 _ENGINES: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
+def _pick_params(model) -> list:
+    try:
+        params = list(model.parameters())
+    except Exception:  # noqa: BLE001
+        return []
+    return params[:: max(1, len(params) // 16)]
+
+
+def _weights_fingerprint(picks) -> tuple:
+    """Cheap change detector for cached engines: (data pointer, version counter, dtype) of a handful of parameters
+    (picked once, when the engine is built). `load_state_dict`, an optimizer step, `.half()` / `.to(dtype)` all move
+    one of these."""
+    return tuple((p.data_ptr(), getattr(p, "_version", 0), str(p.dtype)) for p in picks)
+
+
 def get_engine(model, feature_extractor=None, device=0):
-    """Engine for an HF model object, built on first use from model.state_dict() and cached on the object."""
-    key = (type(feature_extractor).__name__, bool(getattr(feature_extractor, "do_normalize", False)))
+    """Engine for an HF model object, built on first use from model.state_dict() and cached per (model object,
+    feature-extractor kind, CUDA device). The weights are copied at build time; if the model's parameters change
+    afterwards (load_state_dict, fine-tuning, dtype cast) the fingerprint no longer matches and the engine is rebuilt.
+    `invalidate_engine(model)` drops it explicitly."""
+    dev = _device_index(device)
+    key = (type(feature_extractor).__name__, bool(getattr(feature_extractor, "do_normalize", False)), dev)
     per_model = _ENGINES.setdefault(model, {})
-    eng = per_model.get(key)
-    if eng is None:
-        dev = _device_index(device)
-        name = type(model).__name__.lower()
-        if "wavlm" in name:
-            eng = WavLMEngine.from_hf(model, feature_extractor, dev)
-        elif "whisper" in name:
-            eng = WhisperEncoderEngine.from_hf(model, feature_extractor, dev)
-        else:
-            raise TypeError(f"unsupported model type {type(model).__name__}")
-        per_model[key] = eng
+    hit = per_model.get(key)
+    if hit is not None:
+        if _weights_fingerprint(hit[1]) == hit[2]:
+            return hit[0]
+        logger.warning("model parameters changed since the engine was built: rebuilding the engine")
+        hit[0].close()
+    name = type(model).__name__.lower()
+    if "wavlm" in name:
+        eng = WavLMEngine.from_hf(model, feature_extractor, dev)
+    elif "whisper" in name:
+        eng = WhisperEncoderEngine.from_hf(model, feature_extractor, dev)
+    else:
+        raise TypeError(f"unsupported model type {type(model).__name__}")
+    picks = _pick_params(model)
+    per_model[key] = (eng, picks, _weights_fingerprint(picks))
     return eng
+
+
+def invalidate_engine(model=None) -> None:
+    """Drop the cached engine(s) of `model` (all models when None): the next call rebuilds from the current weights."""
+    targets = [model] if model is not None else list(_ENGINES.keys())
+    for m in targets:
+        for hit in _ENGINES.pop(m, {}).values():
+            hit[0].close()
 
 
 def _device_index(device) -> int:
@@ -64,9 +95,9 @@ def _device_index(device) -> int:
     return int(s.split(":")[1]) if ":" in s else 0
 
 
-def load_audio(file_path, target_sr=16000, max_length=None):
-    """Minimal stand-in for the reference's torchaudio loader (REF/WavLM_embeddings.py:87-125; out of scope of the
-    hot path): PCM WAV via the standard library, mono mix-down, optional trim. Returns None on failure."""
+def _read_wav(file_path):
+    """[channels, n] float32 + sample rate from a RIFF/WAVE file without torchaudio: integer PCM through the standard
+    library, IEEE-float (format tag 3, which `wave` refuses) through a minimal chunk walk."""
     try:
         with wave.open(str(file_path), "rb") as w:
             sr, nch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
@@ -75,17 +106,79 @@ def load_audio(file_path, target_sr=16000, max_length=None):
             x = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
         elif width == 4:
             x = np.frombuffer(raw, dtype="<i4").astype(np.float32) / 2147483648.0
+        elif width == 3:
+            b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            x = ((v ^ 0x800000) - 0x800000).astype(np.float32) / 8388608.0
         elif width == 1:
             x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
         else:
             raise ValueError(f"unsupported sample width {width}")
-        if nch > 1:
-            x = x.reshape(-1, nch).mean(axis=1)
-        if sr != target_sr:
-            raise ValueError(f"sample rate {sr} != {target_sr}; resampling is outside the hot path")
+        return x.reshape(-1, nch).T, sr
+    except wave.Error:
+        pass
+    import struct
+
+    with open(str(file_path), "rb") as f:
+        data = f.read()
+    if data[:4] != b"RIFF" or data[8:12] != b"WAVE":
+        raise ValueError("not a RIFF/WAVE file (decode it with torchaudio / convert it to WAV)")
+    pos, fmt, payload = 12, None, None
+    while pos + 8 <= len(data):
+        cid, size = data[pos:pos + 4], struct.unpack("<I", data[pos + 4:pos + 8])[0]
+        body = data[pos + 8:pos + 8 + size]
+        if cid == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", body[:16])
+            if fmt[0] == 0xFFFE and len(body) >= 26:  # WAVE_FORMAT_EXTENSIBLE: the real tag leads the sub-format GUID
+                fmt = (struct.unpack("<H", body[24:26])[0],) + fmt[1:]
+        elif cid == b"data":
+            payload = body
+        pos += 8 + size + (size & 1)
+    if fmt is None or payload is None:
+        raise ValueError("WAV file without fmt / data chunk")
+    tag, nch, sr, _, _, bits = fmt
+    if tag == 3 and bits in (32, 64):
+        x = np.frombuffer(payload, dtype="<f4" if bits == 32 else "<f8").astype(np.float32)
+        return x.reshape(-1, nch).T, sr
+    raise ValueError(f"unsupported WAV format tag {tag} / {bits} bits")
+
+
+def load_audio(file_path, target_sr=16000, max_length=None):
+    """The reference's loader (REF/WavLM_embeddings.py:87-125; REF/whisper_embeddings_large.py has the same one without
+    max_length): torchaudio.load -> mono mix-down -> torchaudio Resample to target_sr -> optional trim ->
+    `.squeeze().numpy()`; any failure is logged and None returned. Where torchaudio cannot decode (this image: its
+    TorchCodec backend is missing) WAV files are read by `_read_wav`; resampling still goes through torchaudio's
+    Resample (pure torch), exactly as in the reference. A file that can be neither decoded nor resampled is skipped
+    with an error line that says why — rows never disappear silently."""
+    try:
+        import torch
+
+        try:
+            import torchaudio
+        except Exception:  # noqa: BLE001
+            torchaudio = None
+        waveform = None
+        if torchaudio is not None:
+            try:
+                waveform, sample_rate = torchaudio.load(file_path)
+            except Exception:  # noqa: BLE001 - no decoder backend: fall through to the WAV reader
+                waveform = None
+        if waveform is None:
+            arr, sample_rate = _read_wav(file_path)
+            waveform = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+        if waveform.shape[0] > 1:
+            waveform = torch.mean(waveform, dim=0, keepdim=True)
+        if sample_rate != target_sr:
+            if torchaudio is None:
+                raise ValueError(f"sample rate {sample_rate} != {target_sr} and torchaudio (Resample) is unavailable")
+            waveform = torchaudio.transforms.Resample(sample_rate, target_sr)(waveform)
         if max_length is not None:
-            x = x[: int(max_length * target_sr)]
-        return np.ascontiguousarray(x, dtype=np.float32)
+            max_samples = int(max_length * target_sr)
+            if waveform.shape[1] > max_samples:
+                logger.info(f"Trimming audio from {waveform.shape[1] / target_sr:.2f}s to {max_length:.2f}s")
+                waveform = waveform[:, :max_samples]
+        logger.debug(f"Audio shape: {waveform.shape}, duration: {waveform.shape[1] / target_sr:.2f}s")
+        return np.ascontiguousarray(waveform.squeeze().numpy(), dtype=np.float32)
     except Exception as e:  # noqa: BLE001 - reference behaviour: log and return None
         logger.error(f"Error loading {file_path}: {e}")
         return None

@@ -137,7 +137,9 @@ def extract_split(rows: Iterable[dict], pooled_fn: Callable[[list], np.ndarray],
             res = dict(row)
             for idx in layer_indices:
                 if idx < p.shape[0]:
-                    res[f"{prefix}{idx}"] = np.ascontiguousarray(p[idx], dtype=np.float32)
+                    # a fresh array per selected layer: a view would keep the whole [B, L+1, D] batch alive for as
+                    # long as `results` lives (all 25 / 33 layers instead of the 3-4 selected)
+                    res[f"{prefix}{idx}"] = np.array(p[idx], dtype=np.float32, copy=True)
                 else:
                     logger.warning(f"Layer {idx} is out of range (max: {p.shape[0] - 1})")
             results.append(res)

@@ -72,6 +72,9 @@ def wavlm_config(name: str):
     if name == "large":
         return WavLMConfig(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
                            feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
+    if name == "large_2l":  # WavLM-Large's shapes at 2 layers: every kernel of the Large step, few launches (ncu captures)
+        return WavLMConfig(hidden_size=1024, num_hidden_layers=2, num_attention_heads=16, intermediate_size=4096,
+                           feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
     if name == "tiny_stable":  # small pre-LN variant for fast tests
         return WavLMConfig(hidden_size=512, num_hidden_layers=3, num_attention_heads=8, intermediate_size=1024,
                            feat_extract_norm="layer", do_stable_layer_norm=True, conv_bias=False)
@@ -81,7 +84,7 @@ def wavlm_config(name: str):
 
 
 def wavlm_do_normalize(name: str) -> bool:
-    return name in ("large", "tiny_stable")
+    return name in ("large", "large_2l", "tiny_stable")
 
 
 def whisper_config(name: str):
@@ -90,6 +93,10 @@ def whisper_config(name: str):
     if name == "large":
         return WhisperConfig(d_model=1280, encoder_layers=32, encoder_attention_heads=20, encoder_ffn_dim=5120,
                              decoder_layers=32, decoder_attention_heads=20, decoder_ffn_dim=5120, num_mel_bins=80,
+                             vocab_size=51865)
+    if name == "large_2l":  # Whisper-large's shapes at 2 layers (ncu captures)
+        return WhisperConfig(d_model=1280, encoder_layers=2, encoder_attention_heads=20, encoder_ffn_dim=5120,
+                             decoder_layers=2, decoder_attention_heads=20, decoder_ffn_dim=5120, num_mel_bins=80,
                              vocab_size=51865)
     if name == "tiny":  # small config for fast tests (d_model must be a multiple of 256, head_dim 64)
         return WhisperConfig(d_model=256, encoder_layers=2, encoder_attention_heads=4, encoder_ffn_dim=1024,

@@ -122,6 +122,59 @@ def test_wav_loader(tmp_path):
     assert load_audio(tmp_path / "missing.wav") is None
 
 
+def test_wav_loader_float_and_resample(tmp_path):
+    """The reference loads ANY sample rate / format torchaudio reads and resamples to 16 kHz
+    (REF/WavLM_embeddings.py:87-125). Here: IEEE-float WAV (which the `wave` module refuses) and an 8 kHz file that
+    must come back resampled by torchaudio's Resample exactly as the reference would do it."""
+    import struct
+
+    import torch
+    import torchaudio
+
+    from ssr_b200.extract import load_audio
+
+    x = (0.5 * np.sin(np.arange(4000) / 7.0)).astype("<f4")
+    p = tmp_path / "f32.wav"
+    hdr = b"RIFF" + struct.pack("<I", 36 + x.nbytes) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 16000,
+                                                                                         64000, 4, 32)
+    p.write_bytes(hdr + b"data" + struct.pack("<I", x.nbytes) + x.tobytes())
+    y = load_audio(p)
+    assert y is not None and y.dtype == np.float32
+    np.testing.assert_array_equal(y, x)
+
+    q = tmp_path / "8k.wav"
+    xi = (np.sin(np.arange(8000) / 9.0) * 12000).astype("<i2")
+    with wave.open(str(q), "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(8000)
+        w.writeframes(xi.tobytes())
+    y8 = load_audio(q)
+    want = torchaudio.transforms.Resample(8000, 16000)(torch.from_numpy(xi.astype(np.float32) / 32768.0)[None])
+    assert y8 is not None and y8.shape == (16000,)
+    np.testing.assert_allclose(y8, want.squeeze().numpy(), atol=1e-6)
+    bad = tmp_path / "bad.flac"
+    bad.write_bytes(b"fLaC" + bytes(64))
+    assert load_audio(bad) is None  # undecodable here: logged and skipped, like the reference
+
+
+def test_bench_config_identical_for_both_arms_and_parity_vectors():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.workload_config(256, 4) == bench.workload_config(256, 4)
+    assert set(bench.workload_config(256, 1)) >= {"workload", "clips_per_gpu_per_step", "parallelism"}
+    ref = np.random.default_rng(0).standard_normal((3, 5, 16)).astype(np.float32)
+    got = ref.copy()
+    got[1, 3] *= 1.02
+    par = bench.parity(got, ref)
+    assert len(par["max_rel_err_per_layer"]) == 5 and len(par["min_cos_per_layer"]) == 5
+    assert par["max_rel_err_per_layer"][3] == pytest.approx(0.02, rel=1e-3) and not par["ok"]
+    assert par["max_rel_err_per_layer"][0] == 0.0
+
+
 GLOO_WORKER = r"""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
