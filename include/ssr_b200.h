@@ -114,6 +114,11 @@ int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples);
  * HF WavLMAttention._relative_positions_bucket, modeling_wavlm.py:252-271, num_buckets 320, max_distance 800).
  * Host function, needs no device; the engine builds its [H, 2R-1] relative-bias table (debug tap "relbias") from it. */
 int32_t ssr_wavlm_rel_bucket(int32_t rel);
+/* Process-wide kernel tuning knobs (A/B measurements, tools/attn_probe.py; engines with a captured CUDA graph keep
+ * the variant they captured until the graph is dropped). Keys: "attention_variant" (bit 0: the softmax warps fetch the
+ * next block's scores from TMEM while working on the current one; bit 1: a quarter of the exponentials on the FMA
+ * pipe; default 3). Returns 0, or -1 for an unknown key. */
+int ssr_tuning_set(const char* key, int32_t value);
 /* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t ssr_launch_count(const ssr_engine* e);
 /* With option "profile" = 1: synchronises, then returns a JSON object

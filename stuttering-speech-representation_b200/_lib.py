@@ -54,6 +54,7 @@ SIGNATURES = {
     "ssr_num_frames": (c_i32, [c_vp, c_i32]),
     "ssr_launch_count": (c_i64, [c_vp]),
     "ssr_wavlm_rel_bucket": (c_i32, [c_i32]),
+    "ssr_tuning_set": (c_i32, [c_cp, c_i32]),
     "ssr_profile_fetch": (c_cp, [c_vp]),
     "ssr_gemm_bf16": (c_i32, [c_i32, c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp,
                               c_i32, c_vp, c_cp, c_i32]),

@@ -86,6 +86,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5 — thirty times
+// below the bf16 rounding P gets anyway): the MUFU unit issues 16 ex2 per clock per SM, which at head_dim 64 is twice
+// the tensor-core time of a block, so a quarter of the exponentials of every row are computed here instead.
+//   t = x + 1.5 * 2^23 rounds x to the nearest integer n in the low mantissa bits; r = x - n in [-0.5, 0.5];
+//   2^x = p(r) * 2^n, the scaling done by adding n to the exponent field.
+// x is clamped to [-125, 126]: below, the result is ~2^-125 (rounds to nothing next to the other terms, and -inf of a
+// masked key lands here too); above, it is >= 2^125, which trips the L_SAFE check exactly like an overflowing MUFU.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fminf(fmaxf(x, -125.0f), 126.0f);
+  const float t = x + 12582912.0f;
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(r, 0.05517164617776871f, 0.2426111251115799f);
+  p = fmaf(p, r, 0.6932609677314758f);
+  p = fmaf(p, r, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // MN-major (here: V, [keys x 64 d], d contiguous) 128B-swizzled operand: 8-row (K) groups are 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -169,7 +186,7 @@ __device__ __forceinline__ Item finish_item(const AttentionArgs& a, const ItemPr
 // col0 .. col0+3 (16-byte units, XOR-swizzled by row % 8 = the UMMA / TMA 128B swizzle).
 // WRITE_BACK keeps the biased / masked scores in `raw`, so that a second pass over the same registers needs neither
 // the bias table nor the mask again.
-template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX = true, bool WRITE_BACK = false>
+template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX = true, bool WRITE_BACK = false, bool POLY = false>
 __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel, float mu2,
                                       float& m_blk, float& l_blk, uint8_t* prow, uint32_t col0) {
   uint32_t packed[16];
@@ -190,8 +207,10 @@ __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, flo
     }
     if (TRACK_MAX) m_blk = fmaxf(m_blk, fmaxf(v0, v1));
     if (WRITE_P) {
-      const float p0 = ex2_approx(fmaf(v0, LOG2E, -mu2));
-      const float p1 = ex2_approx(fmaf(v1, LOG2E, -mu2));
+      // POLY: elements 0, 1 of every 8 (a quarter of the row) take the polynomial instead of the MUFU unit
+      const bool poly = POLY && (k & 6) == 0;
+      const float p0 = poly ? ex2_poly(fmaf(v0, LOG2E, -mu2)) : ex2_approx(fmaf(v0, LOG2E, -mu2));
+      const float p1 = poly ? ex2_poly(fmaf(v1, LOG2E, -mu2)) : ex2_approx(fmaf(v1, LOG2E, -mu2));
       l_blk += p0 + p1;
       __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
       packed[k >> 1] = *reinterpret_cast<uint32_t*>(&pk);
@@ -206,10 +225,13 @@ __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, flo
   }
 }
 
-template <bool HAS_BIAS>
+// VAR bit 0: the softmax warps fetch S of block n+1 from TMEM while they still work on block n (the tcgen05.ld
+// round trip leaves the per-block critical path); bit 1: a quarter of the exponentials on the FMA pipe (ex2_poly).
+template <bool HAS_BIAS, int VAR>
 __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
                     const AttentionArgs a, const int n_items, const Step step) {
+  constexpr bool PIPE = (VAR & 1) != 0, POLY = (VAR & 2) != 0;
   constexpr int KV_STAGES = Lay<HAS_BIAS>::KV_STAGES;
   constexpr int SM_P = Lay<HAS_BIAS>::SM_P;
   constexpr int SM_BAR = Lay<HAS_BIAS>::SM_BAR;
@@ -420,6 +442,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         // for the PV in flight, rescales its 32 rows of O in TMEM and its running sum, and redoes the block.
         constexpr float L_SAFE = 1.8446744e19f * 64.0f;  // 2^70
         float m_ref = -INFINITY, l_run = 0.f;
+        uint32_t r0[32], r1[32];  // scores of the current block (two 32-key chunks)
+        bool have = false;        // PIPE: r0 / r1 were requested from TMEM during the previous block
         for (int j = 0; j < it.nkb; ++j, ++n) {
           const int k0 = j * KBLK;
           const int nlive = min(KBLK, it.len - k0);
@@ -435,10 +459,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             w1 = __ldg(table + min(max(t0 + 32, 0), hi));
             w2 = __ldg(table + min(max(t0 + 64, 0), hi));
           }
-          mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
-          if (threadIdx.x == 0) TR(2, trc);
-          __syncwarp();  // also: every lane is done reading the previous block's window
-          tc_fence_after();
+          if (!have) {
+            mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
+            if (threadIdx.x == 0) TR(2, trc);
+            __syncwarp();  // also: every lane is done reading the previous block's window
+            tc_fence_after();
+            if (warp_live) {
+              tmem_ld_32x32(ts, r0);
+              if (nch == 2) tmem_ld_32x32(ts + 32, r1);
+            }
+          } else {
+            __syncwarp();
+          }
+          // next block of this item: its scores can be fetched while this block is being worked on
+          const bool pre = PIPE && (j + 1 < it.nkb);
+          const int nch_next = pre ? ((min(KBLK, it.len - k0 - KBLK) + 31) >> 5) : 0;
+          const uint32_t ts_next = tmem + lane_addr + TM_S + ((n + 1) & 1) * 64;
           if (warp_live) {
             if (HAS_BIAS) {
               win[lane] = w0;
@@ -447,9 +483,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               __syncwarp();
             }
             float dummy = 0.f, l_blk = 0.f;
-            uint32_t r0[32], r1[32];  // both chunks in flight before the single wait
-            tmem_ld_32x32(ts, r0);
-            if (nch == 2) tmem_ld_32x32(ts + 32, r1);
             tmem_wait_ld();
             if (threadIdx.x == 0) TR(2, trc);
             float mu2;
@@ -463,27 +496,44 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
                 chunk<HAS_BIAS, true, false, true, true>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
               }
               m_ref = m_blk;
-              mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-              chunk<false, false, true, false>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
-              if (nch == 2) chunk<false, false, true, false>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
+            }
+            mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
+            // ---- chunk 0
+            if (j == 0) {
+              chunk<false, false, true, false, false, POLY>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
+            } else if (nch == 2 || !need_mask) {
+              chunk<HAS_BIAS, false, true, false, false, POLY>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
             } else {
-              mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-              if (nch == 2) {
-                chunk<HAS_BIAS, false, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
-                if (need_mask)
-                  chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
-                else
-                  chunk<HAS_BIAS, false, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
+              chunk<HAS_BIAS, true, true, false, false, POLY>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+            }
+            if (pre) {
+              // S of block n+1 was issued before PV of block n-1, i.e. long ago: this wait normally falls through
+              mbar_wait(&bar_s[(n + 1) & 1], ((n + 1) >> 1) & 1);
+              tc_fence_after();
+              tmem_ld_32x32(ts_next, r0);
+            }
+            // ---- chunk 1
+            if (nch == 2) {
+              if (j == 0) {
+                chunk<false, false, true, false, false, POLY>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
+              } else if (need_mask) {
+                chunk<HAS_BIAS, true, true, false, false, POLY>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
               } else {
-                if (need_mask)
-                  chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
-                else
-                  chunk<HAS_BIAS, false, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+                chunk<HAS_BIAS, false, true, false, false, POLY>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
               }
             }
+            if (pre && nch_next == 2) tmem_ld_32x32(ts_next + 32, r1);
             const bool unsafe = !(l_blk < L_SAFE);  // also true for NaN / inf
             if (j > 0 && __any_sync(0xffffffffu, unsafe)) {
-              // rare: raise the reference to this block's exact maximum (rows that do not need it keep theirs)
+              // rare: raise the reference to this block's exact maximum (rows that do not need it keep theirs).
+              // With PIPE the registers already belong to the next block: take this block's scores from TMEM again
+              // (S[n & 1] is not overwritten before this warp's bar_p arrival below).
+              if (pre) {
+                tmem_wait_ld();
+                tmem_ld_32x32(ts, r0);
+                if (nch == 2) tmem_ld_32x32(ts + 32, r1);
+                tmem_wait_ld();
+              }
               float m_blk = -INFINITY, l_dummy = 0.f;
               chunk<HAS_BIAS, true, false>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_dummy, nullptr, 0);
               if (nch == 2) chunk<HAS_BIAS, true, false>(r1, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, l_dummy, nullptr, 0);
@@ -513,12 +563,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               l_blk = 0.f;
               chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
               if (nch == 2) chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
+              if (pre) {  // fetch the next block's scores again
+                tmem_ld_32x32(ts_next, r0);
+                if (nch_next == 2) tmem_ld_32x32(ts_next + 32, r1);
+              }
             }
             l_run += l_blk;
             if (threadIdx.x == 0) TR(2, trc);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             if (threadIdx.x == 0) TR(2, trc);
+          } else if (pre) {
+            // a warp without live rows keeps the barrier protocol going
+            mbar_wait(&bar_s[(n + 1) & 1], ((n + 1) >> 1) & 1);
           }
+          have = pre;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[n & 1]);
@@ -588,6 +646,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
 }  // namespace
 
+// Kernel variant (see attention_tc_kernel: bit 0 = S prefetch, bit 1 = polynomial exp2 share); ssr_tuning_set.
+int g_attention_variant = 3;
+
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err) {
   if (a.D != a.H * HD) {
     err = "attention: head_dim must be 64";
@@ -599,16 +660,22 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   if (make_tmap_2d(&tmkv, a.qkv, 3ULL * a.D, (unsigned long long)a.B * a.slot, 3ULL * a.D, KBLK, err)) return -1;
   static bool attr_set = false;
   static int num_sms = 148;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const AttentionArgs, const int, const Step);
+  static const KernelFn kern[2][4] = {
+      {attention_tc_kernel<false, 0>, attention_tc_kernel<false, 1>, attention_tc_kernel<false, 2>,
+       attention_tc_kernel<false, 3>},
+      {attention_tc_kernel<true, 0>, attention_tc_kernel<true, 1>, attention_tc_kernel<true, 2>,
+       attention_tc_kernel<true, 3>}};
   if (!attr_set) {
-    cudaError_t c1 =
-        cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<true>::SMEM);
-    cudaError_t c2 =
-        cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lay<false>::SMEM);
-    if (c1 != cudaSuccess || c2 != cudaSuccess) {
-      err = std::string("cudaFuncSetAttribute(attention_tc_kernel): ") +
-            cudaGetErrorString(c1 != cudaSuccess ? c1 : c2);
-      return -1;
-    }
+    for (int bsel = 0; bsel < 2; ++bsel)
+      for (int v = 0; v < 4; ++v) {
+        cudaError_t c1 = cudaFuncSetAttribute(kern[bsel][v], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              bsel ? Lay<true>::SMEM : Lay<false>::SMEM);
+        if (c1 != cudaSuccess) {
+          err = std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(c1);
+          return -1;
+        }
+      }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -624,10 +691,9 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   step.dq = grid / (a.B * a.H);
   step.db = (grid % (a.B * a.H)) / a.H;
   step.dh = grid % a.H;
-  if (a.gate != nullptr)
-    attention_tc_kernel<true><<<grid, 192, Lay<true>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);
-  else
-    attention_tc_kernel<false><<<grid, 192, Lay<false>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);
+  const int bsel = a.gate != nullptr ? 1 : 0;
+  const int var = g_attention_variant & 3;
+  kern[bsel][var]<<<grid, 192, bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("attention_tc launch: ") + cudaGetErrorString(ce);

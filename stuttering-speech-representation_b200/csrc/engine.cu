@@ -133,8 +133,10 @@ struct ssr_engine {
   Buf relbias;
   int rel_R = 0;
   // Whisper front end
-  float *twiddle = nullptr, *melw = nullptr;
-  int *mel_lo = nullptr, *mel_hi = nullptr;
+  float *twiddle = nullptr, *melw = nullptr, *dft_tab = nullptr;
+  int *mel_lo = nullptr, *mel_hi = nullptr, *mel_band = nullptr;
+  bf16 *melw_hi = nullptr, *melw_lo = nullptr;
+  int opt_logmel_dense = 0;  // 1: the round-1 dense-DFT log-mel kernel (cross-check)
   bf16 *wc1 = nullptr, *wc2 = nullptr;
   float *bc1 = nullptr, *bc2 = nullptr, *pos_emb = nullptr;
   std::vector<LayerW> layers;
@@ -472,6 +474,53 @@ int create_whisper(ssr_engine* e, WeightMap& w, std::string& err) {
     if (upload(e, mw, &e->melw, err)) return -1;
     if (upload(e, lo, &e->mel_lo, err)) return -1;
     if (upload(e, hi, &e->mel_hi, err)) return -1;
+    // folded-DFT tables (frontend.cu, logmel_folded_kernel): [4][104][104] = {cos, sin} of even k = 2j, then of odd
+    // k = 2j + 1; entry [j][f] = hann[k] * cos|sin(2 pi f k / 400) for k <= 200 (sin: 0 < k < 200), f <= 100; else 0.
+    {
+      std::vector<float> tab((size_t)4 * 104 * 104, 0.f);
+      for (int par = 0; par < 2; ++par)
+        for (int j = 0; j < 104; ++j) {
+          const int k = 2 * j + par;
+          if (k > 200) continue;
+          const double win = 0.5 - 0.5 * cos(2.0 * PI * k / 400.0);
+          for (int f = 0; f <= 100; ++f) {
+            const int ph = (int)(((long long)f * k) % 400);
+            const double ang = 2.0 * PI * ph / 400.0;
+            tab[((size_t)(2 * par) * 104 + j) * 104 + f] = (float)(win * cos(ang));
+            if (k > 0 && k < 200) tab[((size_t)(2 * par + 1) * 104 + j) * 104 + f] = (float)(win * sin(ang));
+          }
+        }
+      if (upload(e, tab, &e->dft_tab, err)) return -1;
+      // filterbank split into bf16 hi + lo, [mel][208]; per 8-mel tile the range of non-zero 16-bin steps
+      std::vector<uint16_t> wh((size_t)NM * 208, 0), wl((size_t)NM * 208, 0);
+      std::vector<int> band(2 * (NM / 8));
+      for (int nt = 0; nt < NM / 8; ++nt) {
+        int blo = 201, bhi = -1;
+        for (int m = nt * 8; m < nt * 8 + 8; ++m) {
+          for (int f = 0; f < 201; ++f) {
+            const float v = mf[(size_t)f * NM + m];
+            const uint16_t h = f2bf(v);
+            uint32_t hu = (uint32_t)h << 16;
+            float hf;
+            memcpy(&hf, &hu, 4);
+            wh[(size_t)m * 208 + f] = h;
+            wl[(size_t)m * 208 + f] = f2bf(v - hf);
+          }
+          if (hi[m] >= lo[m]) {
+            if (lo[m] < blo) blo = lo[m];
+            if (hi[m] > bhi) bhi = hi[m];
+          }
+        }
+        band[2 * nt] = bhi < 0 ? 0 : blo / 16;
+        band[2 * nt + 1] = bhi < 0 ? 0 : bhi / 16 + 1;
+      }
+      uint16_t *dh = nullptr, *dl = nullptr;
+      if (upload(e, wh, &dh, err)) return -1;
+      if (upload(e, wl, &dl, err)) return -1;
+      e->melw_hi = reinterpret_cast<bf16*>(dh);
+      e->melw_lo = reinterpret_cast<bf16*>(dl);
+      if (upload(e, band, &e->mel_band, err)) return -1;
+    }
   }
   if (pack_conv(e, w.get("conv1.weight", (int64_t)D * NM * 3), D, NM, 3, &e->wc1, err)) return -1;
   if (upload_f32(e, w.get("conv1.bias", D), D, &e->bc1, err)) return -1;
@@ -1189,6 +1238,11 @@ int whisper_logmel(ssr_engine* e, const float* audio, int64_t audio_ld, const in
   a.melw = e->melw;
   a.mel_lo = e->mel_lo;
   a.mel_hi = e->mel_hi;
+  a.dft_tab = e->dft_tab;
+  a.melw_hi = e->melw_hi;
+  a.melw_lo = e->melw_lo;
+  a.mel_band = e->mel_band;
+  a.dense = e->opt_logmel_dense;
   a.logspec = e->logspec.as<float>();
   a.gmax = e->gmax.as<unsigned int>();
   a.mel_out = mel_out;
@@ -1471,6 +1525,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_graphs = value;
   else if (k == "conv_ln_fused")
     e->opt_conv_ln_fused = value;
+  else if (k == "logmel_dense")
+    e->opt_logmel_dense = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;
@@ -1724,6 +1780,16 @@ int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples) {
 int64_t ssr_launch_count(const ssr_engine* e) { return e ? e->launches : -1; }
 
 int32_t ssr_wavlm_rel_bucket(int32_t rel) { return rel_bucket(rel); }
+
+int ssr_tuning_set(const char* key, int32_t value) {
+  if (!key) return -1;
+  const std::string k(key);
+  if (k == "attention_variant") {
+    g_attention_variant = value & 3;
+    return 0;
+  }
+  return -1;
+}
 
 int ssr_gemm_bf16(int32_t cuda_device, const void* A, int64_t lda, int64_t a_rows, const void* W, int32_t M,
                   int32_t N, int32_t K, const float* bias, int32_t act, const float* resid, float* out_f32,

@@ -502,6 +502,279 @@ logmel_dft_kernel(const LogMelArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------- folded-DFT log-mel kernel
+// The 400-point real DFT of a frame, decimated twice by hand so that what is left are four dense ~100 x 101 real
+// contractions per frame (40.4 k multiply-adds instead of 161 k for the dense 400 x 402 form):
+//   fold in k (cos even / sin odd about k = 200; the periodic hann window is symmetric, so it folds into the tables)
+//       e[k] = s[k] + s[400-k],  o[k] = s[k] - s[400-k]            (k = 1..199; e[0] = s[0], e[200] = s[200])
+//       Re X[f] = sum_k e[k] w[k] cos(2 pi f k / 400),   Im X[f] = -sum_k o[k] w[k] sin(2 pi f k / 400)
+//   fold in f (f -> 200 - f flips the sign of the odd-k terms of Re and of the even-k terms of Im)
+//       Ae / Ao = even-k / odd-k parts of Re,  Be / Bo = the same of Im, for f = 0..100 only
+//       |X[f]|^2 = (Ae + Ao)^2 + (Be + Bo)^2,    |X[200 - f]|^2 = (Ae - Ao)^2 + (Bo - Be)^2
+// These run as fp32 FMAs (a thread owns 4 frames x 8 f x {Ae, Be, Ao, Bo} = 128 accumulators; folded samples and
+// table rows come from shared memory as 128-bit loads): fp32 throughout keeps the low-level bins of tonal input as
+// accurate as the reference's fp32 FFT, which split-bf16 tensor-core products do not (2^-17 of the LARGEST product).
+// The mel filterbank then is the small tensor-core GEMM: power [64 x 208] x filterbank^T [208 x 80] on mma.sync with
+// power and weights each split into bf16 hi + lo (three products, relative error ~2^-17 of non-negative terms: no
+// cancellation), only over the 16-bin steps where the 8 mels of a tile are non-zero. log10, the per-clip running
+// maximum and a coalesced store of the [64 frames x 80] tile follow in the same kernel; the clamp against the
+// clip-wide maximum needs every frame of the clip and stays in logmel_finish_kernel (its input is L2-resident).
+constexpr int LF = 64;                        // frames per CTA
+constexpr int LX = (LF - 1) * HOP + NFFT;     // staged samples of those frames (overlapping windows): 10480
+constexpr int LJ = 108;                       // pitch of a folded-sample row: >= 104, 4 * odd (mod 32) -> the float4
+                                              // loads of 8 consecutive frames are bank-conflict free
+constexpr int LNF = 104;                      // f columns: 0..100 live, 13 thread groups of 8
+constexpr int LKC = 8;                        // table rows per staged chunk
+constexpr int LNCHUNK = LNF / LKC;            // 13 chunks per parity
+constexpr int LTHREADS = 224;                 // 16 frame groups x 13 f groups = 208 working threads, 7 warps
+constexpr int LP_LD = 216;                    // pitch of the power tile: >= 208, 8 * odd (mod 32)
+constexpr int L_OFF_A = 0;                                // region A: staged samples -> table chunks -> log tile
+constexpr int L_OFF_B = LX;                               // region B: folded samples (4 x [64][108]) -> power tile
+constexpr int L_TAB_CHUNK = 2 * LKC * LNF;                // floats per chunk (cos rows, then sin rows)
+constexpr int LM2_SMEM = (LX + 4 * LF * LJ) * 4;
+static_assert(2 * L_TAB_CHUNK <= LX && LF * NMEL <= LX, "region A is reused for the table ring and the log tile");
+static_assert(LF * LP_LD <= 4 * LF * LJ, "region B is reused for the power tile");
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(LTHREADS, 1)
+logmel_folded_kernel(const LogMelArgs a) {
+  extern __shared__ __align__(16) float lm2[];
+  float* xs = lm2 + L_OFF_A;
+  float* fold = lm2 + L_OFF_B;  // [4][LF][LJ]: Ee (e, even k), Oe (o, even k), Eo, Oo
+  __shared__ float s_max[LTHREADS / 32];
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * LF;
+  int n = a.n_samples[b];
+  if (n > NSAMP) n = NSAMP;
+  const int nlive = live_frames(n);
+  if (f0 >= nlive) return;
+  const float* x = a.audio + (long long)b * a.audio_ld;
+  const int tid = threadIdx.x;
+
+  // ---- stage the samples of the 64 frames: padded index base + i, reflected at both ends of the 30 s window, zero
+  //      beyond the clip. Whole aligned quads inside the clip travel global -> shared as 16-byte cp.async (all of a
+  //      thread's copies in flight at once); the edges (reflection, clip end, unaligned rows) go element by element.
+  {
+    const int base = f0 * HOP - 200;  // multiple of 8
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    for (int q = tid; q < LX / 4; q += LTHREADS) {
+      const int i0 = base + 4 * q;
+      if (vec_ok && i0 >= 0 && i0 + 3 < n) {
+        cp_async16(xs + 4 * q, x + i0);
+      } else {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int idx = i0 + e;
+          if (idx < 0) idx = -idx;
+          if (idx >= NSAMP) idx = 2 * (NSAMP - 1) - idx;
+          t[e] = (idx < n) ? __ldg(x + idx) : 0.f;
+        }
+        *reinterpret_cast<float4*>(xs + 4 * q) = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- fold: row m of buffer {0: Ee, 1: Oe, 2: Eo, 3: Oo}, column j <-> k = 2 j + parity. Pad columns are zero
+  //      (the matching table rows are zero as well; 0 x garbage would not be). One warp per (parity, frame) row.
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int row = warp; row < 2 * LF; row += LTHREADS / 32) {
+      const int par = row >= LF, m = row - par * LF;
+      const float* xm = xs + m * HOP;
+      float* de = fold + ((2 * par) * LF + m) * LJ;
+      float* dO = de + LF * LJ;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < LJ) {
+          const int k = 2 * j + par;
+          float e = 0.f, o = 0.f;
+          if (k <= 200) {
+            const float s1 = xm[k];
+            const float s2 = xm[NFFT - k];  // k = 0 reads xm[400], one past the frame (for the last frame: the first
+                                            // word of region B); the value is discarded by `edge`
+            const bool edge = (k == 0) || (k == 200);
+            e = edge ? s1 : s1 + s2;
+            o = edge ? 0.f : s1 - s2;
+          }
+          de[j] = e;
+          dO[j] = o;
+        }
+      }
+    }
+  }
+  __syncthreads();  // xs is dead from here on: region A becomes the table ring
+
+  // ---- the four contractions. Thread (fg, ng): frames fg + 16 i (i < 4), f = 8 ng + c (c < 8).
+  const int fg = tid & 15, ng = tid >> 4;
+  const bool worker = ng < LNCHUNK;  // 13 f groups; the remaining 16 threads only help with the copies
+  float* ring = lm2 + L_OFF_A;
+  auto issue_chunk = [&](int c) {  // c = 0..25: parity c / 13, rows (c % 13) * 8 .. + 7 of the cos and the sin table
+    const int par = c / LNCHUNK, r0 = (c - par * LNCHUNK) * LKC;
+    const float* gc = a.dft_tab + ((size_t)(2 * par) * LNF + r0) * LNF;       // cos rows (contiguous 8 x 104)
+    const float* gs = a.dft_tab + ((size_t)(2 * par + 1) * LNF + r0) * LNF;   // sin rows
+    float* dst = ring + (c & 1) * L_TAB_CHUNK;
+    constexpr int PIECES = LKC * LNF / 4;  // 208 16-byte pieces per table
+    for (int p = tid; p < 2 * PIECES; p += LTHREADS) {
+      const int t = p >= PIECES, q = p - t * PIECES;
+      cp_async16(dst + t * (LKC * LNF) + 4 * q, (t ? gs : gc) + 4 * q);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float acc[2][2][4][8];  // [parity][cos|sin][frame][f]
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[p][t][i][c] = 0.f;
+
+  issue_chunk(0);
+#pragma unroll
+  for (int par = 0; par < 2; ++par) {
+    const float* Ebuf = fold + (2 * par) * LF * LJ;
+    const float* Obuf = fold + (2 * par + 1) * LF * LJ;
+#pragma unroll 1
+    for (int cc = 0; cc < LNCHUNK; ++cc) {
+      const int c = par * LNCHUNK + cc;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();  // chunk c has landed for everyone; everyone is done with chunk c - 1
+      if (c + 1 < 2 * LNCHUNK) issue_chunk(c + 1);
+      if (worker) {
+        const float* tc = ring + (c & 1) * L_TAB_CHUNK + ng * 8;
+        const float* ts = tc + LKC * LNF;
+#pragma unroll
+        for (int jb = 0; jb < LKC; jb += 4) {
+          float4 e4[4], o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            e4[i] = *reinterpret_cast<const float4*>(Ebuf + (fg + 16 * i) * LJ + cc * LKC + jb);
+            o4[i] = *reinterpret_cast<const float4*>(Obuf + (fg + 16 * i) * LJ + cc * LKC + jb);
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float4 c0 = *reinterpret_cast<const float4*>(tc + (jb + jj) * LNF);
+            const float4 c1 = *reinterpret_cast<const float4*>(tc + (jb + jj) * LNF + 4);
+            const float4 s0 = *reinterpret_cast<const float4*>(ts + (jb + jj) * LNF);
+            const float4 s1 = *reinterpret_cast<const float4*>(ts + (jb + jj) * LNF + 4);
+            const float cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            const float sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float ev = jj == 0 ? e4[i].x : jj == 1 ? e4[i].y : jj == 2 ? e4[i].z : e4[i].w;
+              const float ov = jj == 0 ? o4[i].x : jj == 1 ? o4[i].y : jj == 2 ? o4[i].z : o4[i].w;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                acc[par][0][i][q] = fmaf(ev, cw[q], acc[par][0][i][q]);
+                acc[par][1][i][q] = fmaf(ov, sw[q], acc[par][1][i][q]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();  // every thread is done with the folded samples and the table ring
+
+  // ---- power tile P[frame][bin] (bins 201..215 zero: the mel contraction runs over K = 208)
+  float* P = lm2 + L_OFF_B;
+  for (int i = tid; i < LF * (LP_LD - NBIN); i += LTHREADS) {
+    const int m = i / (LP_LD - NBIN), cpad = i - m * (LP_LD - NBIN);
+    P[m * LP_LD + NBIN + cpad] = 0.f;
+  }
+  if (worker) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = fg + 16 * i;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int f = ng * 8 + q;
+        if (f <= 100) {
+          const float ae = acc[0][0][i][q], be = acc[0][1][i][q], ao = acc[1][0][i][q], bo = acc[1][1][i][q];
+          const float re1 = ae + ao, im1 = be + bo, re2 = ae - ao, im2 = bo - be;
+          P[m * LP_LD + f] = fmaf(re1, re1, im1 * im1);
+          if (f < 100) P[m * LP_LD + 200 - f] = fmaf(re2, re2, im2 * im2);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- mel filterbank on the tensor cores + log10 into the staged [64][80] tile
+  float* ltile = lm2 + L_OFF_A;
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, c = lane & 3;
+    for (int t = warp; t < (LF / 16) * (NMEL / 8); t += LTHREADS / 32) {
+      const int mt = t / (NMEL / 8), nt = t - mt * (NMEL / 8);
+      const int ks0 = __ldg(a.mel_band + 2 * nt), ks1 = __ldg(a.mel_band + 2 * nt + 1);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* p0 = P + (mt * 16 + g) * LP_LD + 2 * c;
+      const float* p1 = p0 + 8 * LP_LD;
+      const bf16* wh = a.melw_hi + (nt * 8 + g) * 208 + 2 * c;
+      const bf16* wl = a.melw_lo + (nt * 8 + g) * 208 + 2 * c;
+      for (int ks = ks0; ks < ks1; ++ks) {
+        const float2 v[4] = {*reinterpret_cast<const float2*>(p0 + ks * 16),
+                             *reinterpret_cast<const float2*>(p1 + ks * 16),
+                             *reinterpret_cast<const float2*>(p0 + ks * 16 + 8),
+                             *reinterpret_cast<const float2*>(p1 + ks * 16 + 8)};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const __nv_bfloat162 h = __floats2bfloat162_rn(v[r].x, v[r].y);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(v[r].x - __low2float(h), v[r].y - __high2float(h));
+          ah[r] = *reinterpret_cast<const uint32_t*>(&h);
+          al[r] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        const uint32_t bh0 = __ldg(reinterpret_cast<const unsigned int*>(wh + ks * 16));
+        const uint32_t bh1 = __ldg(reinterpret_cast<const unsigned int*>(wh + ks * 16 + 8));
+        const uint32_t bl0 = __ldg(reinterpret_cast<const unsigned int*>(wl + ks * 16));
+        const uint32_t bl1 = __ldg(reinterpret_cast<const unsigned int*>(wl + ks * 16 + 8));
+        mma16816(d, al, bh0, bh1);  // small terms first
+        mma16816(d, ah, bl0, bl1);
+        mma16816(d, ah, bh0, bh1);
+      }
+      const int r0 = mt * 16 + g, col = nt * 8 + 2 * c;
+      *reinterpret_cast<float2*>(ltile + r0 * NMEL + col) =
+          make_float2(log10f(fmaxf(d[0], 1e-10f)), log10f(fmaxf(d[1], 1e-10f)));
+      *reinterpret_cast<float2*>(ltile + (r0 + 8) * NMEL + col) =
+          make_float2(log10f(fmaxf(d[2], 1e-10f)), log10f(fmaxf(d[3], 1e-10f)));
+    }
+  }
+  __syncthreads();
+
+  // ---- coalesced store of the live frames (the tile is contiguous in logspec) + per-clip running maximum
+  {
+    const int live = min(LF, nlive - f0);
+    float4* dst = reinterpret_cast<float4*>(a.logspec + ((long long)b * NFRAMES + f0) * NMEL);
+    const float4* src = reinterpret_cast<const float4*>(ltile);
+    float lmax = -INFINITY;
+    for (int i = tid; i < live * (NMEL / 4); i += LTHREADS) {
+      const float4 v = src[i];
+      dst[i] = v;
+      lmax = fmaxf(lmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+    for (int o = 16; o >= 1; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if ((tid & 31) == 0) s_max[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+      float mx = s_max[0];
+      for (int i = 1; i < LTHREADS / 32; ++i) mx = fmaxf(mx, s_max[i]);
+      if (mx > -INFINITY) atomicMax(a.gmax + b, float_to_ordered(mx));
+    }
+  }
+}
+
 __global__ void logmel_init_kernel(unsigned int* gmax, int B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) gmax[i] = float_to_ordered(-INFINITY);
@@ -544,6 +817,8 @@ int launch_logmel(const LogMelArgs& a, cudaStream_t st, std::string& err) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(logmel_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(logmel_folded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM2_SMEM);
     if (ce != cudaSuccess) {
       err = std::string("cudaFuncSetAttribute(logmel): ") + cudaGetErrorString(ce);
       return -1;
@@ -554,9 +829,12 @@ int launch_logmel(const LogMelArgs& a, cudaStream_t st, std::string& err) {
   int ms = a.max_samples > NSAMP ? NSAMP : a.max_samples;
   int max_live = ms <= 0 ? 0 : (ms + 200 + HOP - 1) / HOP;
   if (max_live > NFRAMES) max_live = NFRAMES;
-  if (max_live > 0) {
+  if (max_live > 0 && a.dense) {
     dim3 grid(ceil_div(max_live, LM_FRAMES), a.B);
     logmel_dft_kernel<<<grid, 256, LM_SMEM, st>>>(a);
+  } else if (max_live > 0) {
+    dim3 grid(ceil_div(max_live, LF), a.B);
+    logmel_folded_kernel<<<grid, LTHREADS, LM2_SMEM, st>>>(a);
   }
   dim3 g2(ceil_div(NFRAMES, 32), a.B);
   logmel_finish_kernel<<<g2, 256, 0, st>>>(a);

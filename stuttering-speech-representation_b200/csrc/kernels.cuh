@@ -52,6 +52,7 @@ struct AttentionArgs {
 };
 int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);      // mma.sync (debug / tiny T)
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
+extern int g_attention_variant;  // attention_tc.cu kernel variant (process-wide tuning knob)
 
 // Whisper decoder single-token cross-attention (decoder.cu). All token-level tensors have one row per clip.
 struct DecCrossArgs {
@@ -107,6 +108,13 @@ struct LogMelArgs {
   const float* melw;     // [80, 201] fp32 dense filterbank
   const int* mel_lo;     // [80] first non-zero bin
   const int* mel_hi;     // [80] last non-zero bin
+  // folded-DFT kernel (default): window-folded tables [4][104][104] fp32 = {cos, sin} x {even k, odd k}, the
+  // filterbank split into bf16 hi / lo parts [80][208] and the non-zero 16-bin k-step range of every 8-mel tile
+  const float* dft_tab;
+  const bf16* melw_hi;
+  const bf16* melw_lo;
+  const int* mel_band;   // [10][2] first / one-past-last 16-bin step
+  int dense;             // 1: the round-1 dense-DFT kernel (cross-check)
   float* logspec;        // scratch [B, 3000, 80] fp32 (log10 mel, un-normalised)
   unsigned int* gmax;    // scratch [B] ordered-uint encoding of the per-clip max
   float* mel_out;        // optional [B, 80, 3000] fp32 (HF layout)

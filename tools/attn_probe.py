@@ -40,20 +40,27 @@ def run(name, B, slot, H, length, bias, reps=5):
     diff = (out.float() - ref.float())[live].abs().max().item()
     print(f"{name:8s} max |tc - simt| over live rows = {diff:.3e}", flush=True)
     assert diff < 7e-2, diff  # outputs are bf16: one ulp at |o| in [4, 8) is 3.1e-2
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(reps):
-        call()
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / reps
     fl = 4.0 * B * H * length * length * 64
-    print(f"{name:8s} B={B} slot={slot} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s (live)", flush=True)
+    for variant in (0, 1, 2, 3, 0, 3):
+        lib.ssr_tuning_set(b"attention_variant", variant)
+        call()
+        torch.cuda.synchronize()
+        d = (out.float() - ref.float())[live].abs().max().item()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(reps):
+            call()
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        print(f"{name:8s} variant {variant} B={B} slot={slot} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s "
+              f"(live)  max|tc - simt| {d:.3e}", flush=True)
+    lib.ssr_tuning_set(b"attention_variant", 3)
 
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["wavlm", "whisper"]
     if "wavlm" in which:
-        run("wavlm", 256, 150, 16, 149, True)
+        run("wavlm", 256, 150, 16, 149, True, reps=20)
     if "whisper" in which:
-        run("whisper", 64, 1500, 20, 1500, False, reps=2)
+        run("whisper", 64, 1500, 20, 1500, False, reps=6)
