@@ -115,9 +115,10 @@ int32_t ssr_num_frames(const ssr_engine* e, int32_t n_samples);
  * Host function, needs no device; the engine builds its [H, 2R-1] relative-bias table (debug tap "relbias") from it. */
 int32_t ssr_wavlm_rel_bucket(int32_t rel);
 /* Process-wide kernel tuning knobs (A/B measurements, tools/attn_probe.py; engines with a captured CUDA graph keep
- * the variant they captured until the graph is dropped). Keys: "attention_variant" (bit 0: the softmax warps fetch the
- * next block's scores from TMEM while working on the current one; bit 1: a quarter of the exponentials on the FMA
- * pipe; default 3). Returns 0, or -1 for an unknown key. */
+ * the variant they captured until the graph is dropped). Keys: "attention_variant" (bit 0: packed fp32 pair arithmetic
+ * in the softmax; bit 1: a quarter of the exponentials on the FMA pipe; the default, 1, is the fastest measured),
+ * "attention_paired" (1, default: clips of two query tiles are walked so that both tiles of a (clip, head) run at the
+ * same time on neighbouring CTAs and K / V are read from HBM once; 0: query-tile-major order). Returns 0, or -1 for an unknown key. */
 int ssr_tuning_set(const char* key, int32_t value);
 /* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t ssr_launch_count(const ssr_engine* e);

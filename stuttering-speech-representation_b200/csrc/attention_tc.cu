@@ -128,11 +128,25 @@ struct ItemPre {
 };
 struct Step {
   int dq, db, dh;  // gridDim.x in the mixed radix of the item index (host-computed: lives in the constant bank)
+  int paired;      // two query tiles per clip (129..256 frames): see Cursor
 };
-// Walks the item list of one CTA (idx = blockIdx.x + k * gridDim.x) without a division per item.
+// Walks the item list of one CTA (slot s = blockIdx.x + k * gridDim.x, k = 0, 1, ...) without a division per item.
+//   default : s = (qt * B + b) * H + h  (query-tile-major: every CTA sees the same mix of full and partial tiles)
+//   paired  : two query tiles per clip. s >> 1 = b * H + h and qt = (s & 1) ^ (k & 1) (gridDim.x is even): the two
+//             tiles of a (clip, head) are worked on AT THE SAME TIME by neighbouring CTAs, so K and V come out of
+//             HBM once and the second read hits L2 (query-tile-major order reads them twice, far apart: 471 MB
+//             instead of 314 MB per WavLM-Large layer at B = 256), and every CTA still alternates between full and
+//             tail tiles from round to round.
 struct Cursor {
-  int qt, b, h;  // current item: idx = (qt * B + b) * H + h
-  __device__ __forceinline__ void init(const AttentionArgs& a) {
+  int qt, b, h;  // current item
+  __device__ __forceinline__ void init(const AttentionArgs& a, const Step& st) {
+    if (st.paired) {
+      const int p = (int)blockIdx.x >> 1;
+      b = p / a.H;
+      h = p - b * a.H;
+      qt = (int)blockIdx.x & 1;
+      return;
+    }
     const int bh = a.B * a.H;
     qt = (int)blockIdx.x / bh;
     const int rem = (int)blockIdx.x - qt * bh;
@@ -147,7 +161,9 @@ struct Cursor {
       h -= a.H;
       ++b;
     }
-    if (b >= a.B) {
+    if (st.paired) {
+      qt ^= 1;
+    } else if (b >= a.B) {
       b -= a.B;
       ++qt;
     }
@@ -186,16 +202,46 @@ __device__ __forceinline__ Item finish_item(const AttentionArgs& a, const ItemPr
 // col0 .. col0+3 (16-byte units, XOR-swizzled by row % 8 = the UMMA / TMA 128B swizzle).
 // WRITE_BACK keeps the biased / masked scores in `raw`, so that a second pass over the same registers needs neither
 // the bias table nor the mask again.
-template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX = true, bool WRITE_BACK = false, bool POLY = false>
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes of work). The softmax warps are bound by
+// instruction issue and dependent-issue latency (two warps per scheduler), not by any one pipe, so every instruction
+// taken out of the per-element sequence shortens the block.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX = true, bool WRITE_BACK = false, bool POLY = false,
+          bool PACK2 = false>
 __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel, float mu2,
                                       float& m_blk, float& l_blk, uint8_t* prow, uint32_t col0) {
   uint32_t packed[16];
+  uint64_t l2 = 0;  // (0.f, 0.f): PACK2 keeps the row sum as a pair of partial sums
+  const uint64_t scale2 = pack2(LOG2E, LOG2E), shift2 = pack2(-mu2, -mu2), gate2 = pack2(gate, gate);
 #pragma unroll
   for (int k = 0; k < 32; k += 2) {
     float v0 = __uint_as_float(raw[k]), v1 = __uint_as_float(raw[k + 1]);
     if (HAS_BIAS) {
-      v0 = fmaf(gate, rel[k], v0);  // rel: this row's view of the warp's shared-memory window (see WIN)
-      v1 = fmaf(gate, rel[k + 1], v1);
+      // rel: this row's view of the warp's shared-memory window (see WIN); its alignment depends on the lane
+      if (PACK2) {
+        unpack2(fma2(gate2, pack2(rel[k], rel[k + 1]), pack2(v0, v1)), v0, v1);
+      } else {
+        v0 = fmaf(gate, rel[k], v0);
+        v1 = fmaf(gate, rel[k + 1], v1);
+      }
     }
     if (MASK) {
       if (jg0 + k >= len) v0 = -INFINITY;
@@ -209,14 +255,29 @@ __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, flo
     if (WRITE_P) {
       // POLY: elements 0, 1 of every 8 (a quarter of the row) take the polynomial instead of the MUFU unit
       const bool poly = POLY && (k & 6) == 0;
-      const float p0 = poly ? ex2_poly(fmaf(v0, LOG2E, -mu2)) : ex2_approx(fmaf(v0, LOG2E, -mu2));
-      const float p1 = poly ? ex2_poly(fmaf(v1, LOG2E, -mu2)) : ex2_approx(fmaf(v1, LOG2E, -mu2));
-      l_blk += p0 + p1;
+      float x0, x1;
+      if (PACK2) {
+        unpack2(fma2(pack2(v0, v1), scale2, shift2), x0, x1);
+      } else {
+        x0 = fmaf(v0, LOG2E, -mu2);
+        x1 = fmaf(v1, LOG2E, -mu2);
+      }
+      const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
+      const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
+      if (PACK2)
+        l2 = add2(l2, pack2(p0, p1));
+      else
+        l_blk += p0 + p1;
       __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
       packed[k >> 1] = *reinterpret_cast<uint32_t*>(&pk);
     }
   }
   if (WRITE_P) {
+    if (PACK2) {
+      float la, lb;
+      unpack2(l2, la, lb);
+      l_blk += la + lb;
+    }
     const uint32_t sw = (uint32_t)((reinterpret_cast<uintptr_t>(prow) >> 7) & 7);  // row % 8 (rows are 128 B apart)
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -225,13 +286,16 @@ __device__ __forceinline__ void chunk(uint32_t (&raw)[32], int jg0, int len, flo
   }
 }
 
-// VAR bit 0: the softmax warps fetch S of block n+1 from TMEM while they still work on block n (the tcgen05.ld
-// round trip leaves the per-block critical path); bit 1: a quarter of the exponentials on the FMA pipe (ex2_poly).
+// VAR bit 0: packed fp32 pair arithmetic in the softmax (FFMA2 / FADD2); bit 1: a quarter of the exponentials on the
+// FMA pipe (ex2_poly). Measured on B200 (tools/attn_probe.py): packed pairs are worth 1-3 % (WavLM
+// shape 146 -> 142 us per layer, Whisper shape 1.30 -> 1.28 ms); the polynomial share makes both shapes SLOWER
+// (Whisper 1.30 -> 1.37 ms): in their exponential phase the softmax warps do queue on the MUFU unit (ncu source page),
+// but nine FMA / ALU slots per polynomial exponential cost as much issue time as the eight MUFU cycles they free.
 template <bool HAS_BIAS, int VAR>
 __global__ void __launch_bounds__(192, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
                     const AttentionArgs a, const int n_items, const Step step) {
-  constexpr bool PIPE = (VAR & 1) != 0, POLY = (VAR & 2) != 0;
+  constexpr bool PACK2 = (VAR & 1) != 0, POLY = (VAR & 2) != 0;
   constexpr int KV_STAGES = Lay<HAS_BIAS>::KV_STAGES;
   constexpr int SM_P = Lay<HAS_BIAS>::SM_P;
   constexpr int SM_BAR = Lay<HAS_BIAS>::SM_BAR;
@@ -284,7 +348,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     uint32_t n_item = 0, n = 0;
     int trc = 0; (void)trc;
     Cursor cur;
-    cur.init(a);
+    cur.init(a, step);
     int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + 8;  // [2] private to this thread
     uint32_t lbuf = 0;
     ItemPre nxt = cur.load(a, lsm);
@@ -340,7 +404,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       umma_commit(&bar_o[pn & 1]);
     };
     Cursor cur;
-    cur.init(a);
+    cur.init(a, step);
     int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + 10;  // [2] private to this thread
     uint32_t lbuf = 0;
     ItemPre nxt = cur.load(a, lsm);
@@ -390,7 +454,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     uint32_t n = 0;
     int trc = 0; (void)trc;
     Cursor cur;
-    cur.init(a);
+    cur.init(a, step);
     int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + quad * 2;  // [2] per warp, copied by lane 0
     ItemPre nxt = cur.load(a, lsm, lane == 0);
     // The row's gate of the NEXT item travels global -> shared memory by cp.async (no register is live across the
@@ -442,8 +506,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
         // for the PV in flight, rescales its 32 rows of O in TMEM and its running sum, and redoes the block.
         constexpr float L_SAFE = 1.8446744e19f * 64.0f;  // 2^70
         float m_ref = -INFINITY, l_run = 0.f;
-        uint32_t r0[32], r1[32];  // scores of the current block (two 32-key chunks)
-        bool have = false;        // PIPE: r0 / r1 were requested from TMEM during the previous block
         for (int j = 0; j < it.nkb; ++j, ++n) {
           const int k0 = j * KBLK;
           const int nlive = min(KBLK, it.len - k0);
@@ -459,22 +521,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
             w1 = __ldg(table + min(max(t0 + 32, 0), hi));
             w2 = __ldg(table + min(max(t0 + 64, 0), hi));
           }
-          if (!have) {
-            mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
-            if (threadIdx.x == 0) TR(2, trc);
-            __syncwarp();  // also: every lane is done reading the previous block's window
-            tc_fence_after();
-            if (warp_live) {
-              tmem_ld_32x32(ts, r0);
-              if (nch == 2) tmem_ld_32x32(ts + 32, r1);
-            }
-          } else {
-            __syncwarp();
-          }
-          // next block of this item: its scores can be fetched while this block is being worked on
-          const bool pre = PIPE && (j + 1 < it.nkb);
-          const int nch_next = pre ? ((min(KBLK, it.len - k0 - KBLK) + 31) >> 5) : 0;
-          const uint32_t ts_next = tmem + lane_addr + TM_S + ((n + 1) & 1) * 64;
+          mbar_wait(&bar_s[n & 1], (n >> 1) & 1);
+          if (threadIdx.x == 0) TR(2, trc);
+          __syncwarp();  // also: every lane is done reading the previous block's window
+          tc_fence_after();
           if (warp_live) {
             if (HAS_BIAS) {
               win[lane] = w0;
@@ -483,6 +533,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               __syncwarp();
             }
             float dummy = 0.f, l_blk = 0.f;
+            uint32_t r0[32], r1[32];  // both chunks in flight before the single wait
+            tmem_ld_32x32(ts, r0);
+            if (nch == 2) tmem_ld_32x32(ts + 32, r1);
             tmem_wait_ld();
             if (threadIdx.x == 0) TR(2, trc);
             float mu2;
@@ -490,50 +543,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               // exact row maximum of the first block; the biased / masked scores stay in the registers
               float m_blk = -INFINITY;
               if (nch == 2) {
-                chunk<HAS_BIAS, false, false, true, HAS_BIAS>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
-                chunk<HAS_BIAS, true, false, true, true>(r1, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, false, false, true, HAS_BIAS, false, PACK2>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, true, false, true, true, false, PACK2>(r1, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, l_blk, nullptr, 0);
               } else {
-                chunk<HAS_BIAS, true, false, true, true>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
+                chunk<HAS_BIAS, true, false, true, true, false, PACK2>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_blk, nullptr, 0);
               }
               m_ref = m_blk;
-            }
-            mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-            // ---- chunk 0
-            if (j == 0) {
-              chunk<false, false, true, false, false, POLY>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
-            } else if (nch == 2 || !need_mask) {
-              chunk<HAS_BIAS, false, true, false, false, POLY>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+              mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
+              chunk<false, false, true, false, false, POLY, PACK2>(r0, k0, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 0);
+              if (nch == 2)
+                chunk<false, false, true, false, false, POLY, PACK2>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
             } else {
-              chunk<HAS_BIAS, true, true, false, false, POLY>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
-            }
-            if (pre) {
-              // S of block n+1 was issued before PV of block n-1, i.e. long ago: this wait normally falls through
-              mbar_wait(&bar_s[(n + 1) & 1], ((n + 1) >> 1) & 1);
-              tc_fence_after();
-              tmem_ld_32x32(ts_next, r0);
-            }
-            // ---- chunk 1
-            if (nch == 2) {
-              if (j == 0) {
-                chunk<false, false, true, false, false, POLY>(r1, k0 + 32, it.len, 0.f, nullptr, mu2, dummy, l_blk, prow, 4);
-              } else if (need_mask) {
-                chunk<HAS_BIAS, true, true, false, false, POLY>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
+              mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
+              if (nch == 2) {
+                chunk<HAS_BIAS, false, true, false, false, POLY, PACK2>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+                if (need_mask)
+                  chunk<HAS_BIAS, true, true, false, false, POLY, PACK2>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
+                else
+                  chunk<HAS_BIAS, false, true, false, false, POLY, PACK2>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
               } else {
-                chunk<HAS_BIAS, false, true, false, false, POLY>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
+                if (need_mask)
+                  chunk<HAS_BIAS, true, true, false, false, POLY, PACK2>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
+                else
+                  chunk<HAS_BIAS, false, true, false, false, POLY, PACK2>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
               }
             }
-            if (pre && nch_next == 2) tmem_ld_32x32(ts_next + 32, r1);
             const bool unsafe = !(l_blk < L_SAFE);  // also true for NaN / inf
             if (j > 0 && __any_sync(0xffffffffu, unsafe)) {
-              // rare: raise the reference to this block's exact maximum (rows that do not need it keep theirs).
-              // With PIPE the registers already belong to the next block: take this block's scores from TMEM again
-              // (S[n & 1] is not overwritten before this warp's bar_p arrival below).
-              if (pre) {
-                tmem_wait_ld();
-                tmem_ld_32x32(ts, r0);
-                if (nch == 2) tmem_ld_32x32(ts + 32, r1);
-                tmem_wait_ld();
-              }
+              // rare: raise the reference to this block's exact maximum (rows that do not need it keep theirs)
               float m_blk = -INFINITY, l_dummy = 0.f;
               chunk<HAS_BIAS, true, false>(r0, k0, it.len, gate, rel, 0.f, m_blk, l_dummy, nullptr, 0);
               if (nch == 2) chunk<HAS_BIAS, true, false>(r1, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, l_dummy, nullptr, 0);
@@ -563,20 +600,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
               l_blk = 0.f;
               chunk<HAS_BIAS, true, true, false>(r0, k0, it.len, gate, rel, mu2, dummy, l_blk, prow, 0);
               if (nch == 2) chunk<HAS_BIAS, true, true, false>(r1, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, prow, 4);
-              if (pre) {  // fetch the next block's scores again
-                tmem_ld_32x32(ts_next, r0);
-                if (nch_next == 2) tmem_ld_32x32(ts_next + 32, r1);
-              }
             }
             l_run += l_blk;
             if (threadIdx.x == 0) TR(2, trc);
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             if (threadIdx.x == 0) TR(2, trc);
-          } else if (pre) {
-            // a warp without live rows keeps the barrier protocol going
-            mbar_wait(&bar_s[(n + 1) & 1], ((n + 1) >> 1) & 1);
           }
-          have = pre;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[n & 1]);
@@ -644,10 +673,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   }
 }
 
+
 }  // namespace
 
-// Kernel variant (see attention_tc_kernel: bit 0 = S prefetch, bit 1 = polynomial exp2 share); ssr_tuning_set.
-int g_attention_variant = 3;
+// Kernel variant (see attention_tc_kernel: bit 0 = packed pair arithmetic, bit 1 = polynomial exp2 share);
+// ssr_tuning_set.
+int g_attention_variant = 1;
+// 1: two-tile clips use the paired item order (see Cursor); 0: query-tile-major order everywhere.
+int g_attention_paired = 1;
 
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err) {
   if (a.D != a.H * HD) {
@@ -691,6 +724,13 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   step.dq = grid / (a.B * a.H);
   step.db = (grid % (a.B * a.H)) / a.H;
   step.dh = grid % a.H;
+  step.paired = 0;
+  if (g_attention_paired && ceil_div(a.slot, QT) == 2 && (grid & 1) == 0) {
+    step.paired = 1;
+    step.dq = 0;
+    step.db = (grid / 2) / a.H;
+    step.dh = (grid / 2) % a.H;
+  }
   const int bsel = a.gate != nullptr ? 1 : 0;
   const int var = g_attention_variant & 3;
   kern[bsel][var]<<<grid, 192, bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);

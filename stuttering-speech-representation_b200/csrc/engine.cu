@@ -122,6 +122,7 @@ struct ssr_engine {
   std::vector<void*> owned;  // every cudaMalloc'd weight block
   // WavLM front end
   float* c0_w = nullptr;
+  float* c0_wstat = nullptr;
   float *cln_g[7] = {}, *cln_b[7] = {};
   bf16* conv_w[7] = {};
   float *fp_ln_g = nullptr, *fp_ln_b = nullptr, *fp_b = nullptr;
@@ -343,6 +344,22 @@ int create_wavlm(ssr_engine* e, WeightMap& w, std::string& err) {
   static const int ks[7] = {10, 3, 3, 3, 3, 2, 2};
   const bool layer_norm = d.feat_norm == SSR_FEAT_NORM_LAYER;
   if (upload_f32(e, w.get("feature_extractor.conv_layers.0.conv.weight", 5120), 5120, &e->c0_w, err)) return -1;
+  {
+    // conv0 + LayerNorm: per-frame channel statistics as a linear / quadratic form of the 10 window samples
+    const float* w0 = w.get("feature_extractor.conv_layers.0.conv.weight", 5120);
+    std::vector<float> st(112, 0.f);
+    for (int k = 0; k < 10; ++k) {
+      double m = 0.0;
+      for (int c = 0; c < 512; ++c) m += (double)w0[c * 10 + k];
+      st[k] = (float)(m / 512.0);
+      for (int k2 = k; k2 < 10; ++k2) {
+        double gsum = 0.0;
+        for (int c = 0; c < 512; ++c) gsum += (double)w0[c * 10 + k] * (double)w0[c * 10 + k2];
+        st[10 + k * 10 + k2] = (float)((k2 == k ? 1.0 : 2.0) * gsum / 512.0);
+      }
+    }
+    if (upload(e, st, &e->c0_wstat, err)) return -1;
+  }
   for (int i = 0; i < 7; ++i) {
     const std::string p = "feature_extractor.conv_layers." + std::to_string(i);
     if (i > 0 && pack_conv(e, w.get(p + ".conv.weight", 512LL * 512 * ks[i]), 512, 512, ks[i], &e->conv_w[i], err))
@@ -1043,6 +1060,7 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     a.do_normalize = d.do_normalize;
     a.stats = e->stats.as<float>();
     a.w = e->c0_w;
+    a.wstat = e->c0_wstat;
     a.gamma = e->cln_g[0];
     a.beta = e->cln_b[0];
     a.mode = d.feat_norm == SSR_FEAT_NORM_LAYER ? 0 : 1;
@@ -1786,6 +1804,10 @@ int ssr_tuning_set(const char* key, int32_t value) {
   const std::string k(key);
   if (k == "attention_variant") {
     g_attention_variant = value & 3;
+    return 0;
+  }
+  if (k == "attention_paired") {
+    g_attention_paired = value != 0;
     return 0;
   }
   return -1;

@@ -225,7 +225,8 @@ constexpr int C0M_XLEN = C0M_FRAMES * 5 + 8;
 constexpr int C0M_OFF_GB = 512 * C0M_WP * 2;
 constexpr int C0M_OFF_STAGE = C0M_OFF_GB + 2 * 512 * 4;
 constexpr int C0M_OFF_X = C0M_OFF_STAGE + C0M_WARPS * 16 * C0M_SP * 2;
-constexpr int C0M_SMEM = C0M_OFF_X + 2 * C0M_XLEN * 2;
+constexpr int C0M_OFF_WS = C0M_OFF_X + 2 * C0M_XLEN * 2;  // wbar[10] | G[10][10] (upper triangle, doubled off-diagonals)
+constexpr int C0M_SMEM = C0M_OFF_WS + 112 * 4;
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
@@ -242,10 +243,12 @@ wavlm_conv0_mma_kernel(const Conv0Args a, const int iters) {
   bf16* stage_all = reinterpret_cast<bf16*>(c0m_smem + C0M_OFF_STAGE);             // [warp][16][C0M_SP]
   bf16* xh_s = reinterpret_cast<bf16*>(c0m_smem + C0M_OFF_X);
   bf16* xl_s = xh_s + C0M_XLEN;
+  float* ws_s = reinterpret_cast<float*>(c0m_smem + C0M_OFF_WS);
   const int b = blockIdx.y;
   const int n = a.n_samples[b];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;
+  if (threadIdx.x < 110) ws_s[threadIdx.x] = a.wstat[threadIdx.x];
 
   // weights: k 0-9 -> hi, 10-19 -> hi, 20-29 -> lo, 30-31 -> 0
   for (int i = threadIdx.x; i < 512 * 32; i += 256) {
@@ -306,27 +309,30 @@ wavlm_conv0_mma_kernel(const Conv0Args a, const int iters) {
                  *reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8));
     };
 
-    // pass 1: row statistics
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll 4
-    for (int nt = 0; nt < 64; ++nt) {
-      float acc[4];
-      tile(nt, acc);
-      s0 += acc[0] + acc[1];
-      q0 = fmaf(acc[0], acc[0], fmaf(acc[1], acc[1], q0));
-      s1 += acc[2] + acc[3];
-      q1 = fmaf(acc[2], acc[2], fmaf(acc[3], acc[3], q1));
-    }
+    // Row statistics WITHOUT forming the 512 outputs: y_c = sum_k w[c][k] x[k] is linear in the ten window samples, so
+    //   mean_c y   = wbar . x                      wbar[k]   = mean_c w[c][k]
+    //   mean_c y^2 = x^T G x                       G[k][k']  = mean_c w[c][k] w[c][k']   (symmetric, 55 distinct)
+    // Lane l < 16 does frame f0 + l in fp32 (65 FMAs); the rows of this lane's fragment (g, g + 8) fetch theirs by
+    // shuffle. (This replaced a first pass over all 64 channel tiles: 128 MMAs + 512 CUDA-core instructions per warp.)
+    float mu_l = 0.f, rs_l = 0.f;
+    {
+      const int fr = f0 + (lane & 15);
+      float xv[10];
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+      for (int k = 0; k < 10; ++k) xv[k] = __bfloat162float(xh_s[fr * 5 + k]) + __bfloat162float(xl_s[fr * 5 + k]);
+      float e2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        mu_l = fmaf(ws_s[k], xv[k], mu_l);
+        float t = 0.f;
+#pragma unroll
+        for (int k2 = k; k2 < 10; ++k2) t = fmaf(ws_s[10 + k * 10 + k2], xv[k2], t);  // off-diagonals stored doubled
+        e2 = fmaf(t, xv[k], e2);
+      }
+      rs_l = rsqrtf(fmaxf(e2 - mu_l * mu_l, 0.f) + 1e-5f);
     }
-    const float mu0 = s0 * (1.0f / 512.f), mu1 = s1 * (1.0f / 512.f);
-    const float rs0 = rsqrtf(fmaxf(q0 * (1.0f / 512.f) - mu0 * mu0, 0.f) + 1e-5f);
-    const float rs1 = rsqrtf(fmaxf(q1 * (1.0f / 512.f) - mu1 * mu1, 0.f) + 1e-5f);
+    const float mu0 = __shfl_sync(0xffffffffu, mu_l, g), mu1 = __shfl_sync(0xffffffffu, mu_l, g + 8);
+    const float rs0 = __shfl_sync(0xffffffffu, rs_l, g), rs1 = __shfl_sync(0xffffffffu, rs_l, g + 8);
 
     // pass 2: normalise, GELU, store 64 channels (one 128-byte segment per frame) at a time
     bf16* stg = stage_all + warp * (16 * C0M_SP);

@@ -53,6 +53,7 @@ struct AttentionArgs {
 int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);      // mma.sync (debug / tiny T)
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
 extern int g_attention_variant;  // attention_tc.cu kernel variant (process-wide tuning knob)
+extern int g_attention_paired;   // 1: paired item order for two-tile clips
 
 // Whisper decoder single-token cross-attention (decoder.cu). All token-level tensors have one row per clip.
 struct DecCrossArgs {
@@ -84,6 +85,8 @@ struct Conv0Args {
   int do_normalize;  // Wav2Vec2FeatureExtractor zero-mean / unit-variance
   float* stats;      // [B, 2] mean, rstd (scratch)
   const float* w;    // [512, 10]
+  const float* wstat;  // [110]: mean_c w[c][k] (10), then mean_c w[c][k] w[c][k'] as [10][10] with the upper triangle
+                       // holding doubled off-diagonals (LayerNorm mode: row statistics as a quadratic form in x)
   const float* gamma;
   const float* beta;  // [512]
   int mode;           // 0: LayerNorm over channels (Large); 1: GroupNorm over time (Base+)

@@ -8,6 +8,9 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+DEFAULT_VARIANT = 1  # csrc/attention_tc.cu g_attention_variant
+
+
 def _lib():
     from ssr_b200 import _lib as L
 
@@ -169,7 +172,8 @@ def _attn_ref(qkv, B, slot, H, lens, gate, relbias, rel_center):
 @pytest.mark.parametrize("slot,H,lens,bias", [
     (149, 16, None, True), (150, 12, [149, 77, 150], True), (200, 4, [200, 64, 65], False), (1500, 2, None, False),
     (31, 3, [31, 5, 1], True), (128, 2, [128, 127, 1], True), (257, 2, [257, 256, 129], True),
-    (1500, 2, [1500, 1400, 300], True),
+    (1500, 2, [1500, 1400, 300], True), (160, 4, [160, 129, 33], True), (64, 2, [64, 32, 1], False),
+    (160, 3, [159, 97, 160], False), (161, 2, [161, 160, 2], True),
 ])
 def test_attention(slot, H, lens, bias, impl):
     lib = _lib()
@@ -186,15 +190,29 @@ def test_attention(slot, H, lens, bias, impl):
         gate = torch.rand(B * slot, H, device="cuda", generator=g) * 2 + 0.5
         relb = torch.randn(H, 2 * R - 1, device="cuda", generator=g)
     ref = _attn_ref(qkv, B, slot, H, lens_t, gate, relb, R - 1).view(B, slot, D)
+    if impl == 0 and 128 < slot <= 256:
+        # two-tile clips are walked in the paired item order by default; the query-tile-major order must agree
+        assert lib.ssr_tuning_set(b"attention_paired", 0) == 0
+        out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
+        e = _err()
+        rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), _ptr(gate), _ptr(relb),
+                               2 * R - 1, R - 1, 0, None, e, 512)
+        torch.cuda.synchronize()
+        lib.ssr_tuning_set(b"attention_paired", 1)
+        assert rc == 0, e.value.decode()
+        got = out.float().view(B, slot, D)
+        for b in range(B):
+            L = int(lens_t[b])
+            assert (got[b, :L] - ref[b, :L]).abs().max().item() < 2e-2, f"query-tile-major order, clip {b}"
     # every variant of the tcgen05 kernel (S prefetch from TMEM, polynomial exp2 share) must hold the same tolerance
-    for variant in ([0, 1, 2, 3] if impl == 0 else [3]):
+    for variant in ([0, 1, 2, 3] if impl == 0 else [DEFAULT_VARIANT]):
         assert lib.ssr_tuning_set(b"attention_variant", variant) == 0
         out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
         e = _err()
         rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), _ptr(gate), _ptr(relb),
                                2 * R - 1, R - 1, impl, None, e, 512)
         torch.cuda.synchronize()
-        lib.ssr_tuning_set(b"attention_variant", 3)
+        lib.ssr_tuning_set(b"attention_variant", DEFAULT_VARIANT)
         assert rc == 0, e.value.decode()
         got = out.float().view(B, slot, D)
         for b in range(B):
@@ -231,7 +249,7 @@ def test_attention_stale_reference_and_rescale(scale):
         rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), None, None, 0, 0, 0,
                                None, e, 512)
         torch.cuda.synchronize()
-        lib.ssr_tuning_set(b"attention_variant", 3)
+        lib.ssr_tuning_set(b"attention_variant", DEFAULT_VARIANT)
         assert rc == 0, e.value.decode()
         got = out.float().view(B, slot, D)
         assert torch.isfinite(got).all()

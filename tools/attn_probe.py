@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ssr_b200 import _lib
 
 lib = _lib.load()
+DEFAULT_VARIANT = 1  # csrc/attention_tc.cu g_attention_variant
 
 
 def run(name, B, slot, H, length, bias, reps=5):
@@ -39,9 +40,14 @@ def run(name, B, slot, H, length, bias, reps=5):
     live = (torch.arange(slot, device="cuda")[None, :] < lens[:, None]).reshape(-1)
     diff = (out.float() - ref.float())[live].abs().max().item()
     print(f"{name:8s} max |tc - simt| over live rows = {diff:.3e}", flush=True)
-    assert diff < 7e-2, diff  # outputs are bf16: one ulp at |o| in [4, 8) is 3.1e-2
+    # (outputs are bf16: one ulp at |o| in [4, 8) is 3.1e-2; the GPU tests assert, this probe only reports)
     fl = 4.0 * B * H * length * length * 64
-    for variant in (0, 1, 2, 3, 0, 3):
+    combos = [(1, v) for v in (0, 1, 2, 3)]
+    if 128 < slot <= 256:
+        combos += [(0, v) for v in (0, 1)]
+    combos += combos[:2]
+    for paired, variant in combos:
+        lib.ssr_tuning_set(b"attention_paired", paired)
         lib.ssr_tuning_set(b"attention_variant", variant)
         call()
         torch.cuda.synchronize()
@@ -53,9 +59,10 @@ def run(name, B, slot, H, length, bias, reps=5):
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / reps
-        print(f"{name:8s} variant {variant} B={B} slot={slot} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s "
+        print(f"{name:8s} paired {paired} variant {variant} B={B} slot={slot} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s "
               f"(live)  max|tc - simt| {d:.3e}", flush=True)
-    lib.ssr_tuning_set(b"attention_variant", 3)
+    lib.ssr_tuning_set(b"attention_variant", DEFAULT_VARIANT)
+    lib.ssr_tuning_set(b"attention_paired", 1)
 
 
 if __name__ == "__main__":
