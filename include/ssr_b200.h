@@ -73,6 +73,10 @@ const char* ssr_last_error(const ssr_engine* e);
  * "attn_simt" (1 = mma.sync attention cross-check kernel), "posconv_generic" (1 = positional conv through the generic
  * GEMM), "graphs" (default 1: the *_host entry points replay a captured CUDA graph when a small batch (B <= 16)
  * repeats the previous call's batch size, pitch and lengths — the reference's per-clip loop over equal-length clips),
+ * "host_pipeline" (default 1: the *_host entry points move a batch of >= 64 clips host -> device in chunks on a copy
+ * stream while the front end already runs on the chunks that have landed, and copy the pooled rows of
+ * hidden_states[0 .. L-1] back while the last layer still computes), "logmel_dense" (1 = the dense-DFT log-mel kernel,
+ * a cross-check of the default folded-DFT one), "conv_ln_fused" (default 1),
  * "profile" (1 = bracket every kernel launch with CUDA events on the launching stream; read with ssr_profile_fetch).
  * Returns 0, or -1 for an unknown key. */
 int ssr_set_option(ssr_engine* e, const char* key, int32_t value);

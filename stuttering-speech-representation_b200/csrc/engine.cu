@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <map>
 #include <memory>
@@ -173,6 +174,19 @@ struct ssr_engine {
   cudaEvent_t last_done = nullptr;
   cudaStream_t last_stream = nullptr;
   bool last_valid = false;
+  // Host-entry pipeline for large batches (the synchronous *_host call is the end-to-end headline): the batch's
+  // audio travels host -> device in chunks on a copy stream while conv0 / conv1 of the chunks that have landed already
+  // run, and the pooled rows of hidden_states[0 .. L-1] travel device -> host while the last layer still computes.
+  struct HostPipe {
+    bool active = false;        // set by run_host around one forward
+    int n_chunks = 0, chunk_clips = 0;
+    cudaEvent_t h2d_done[8] = {};
+    cudaEvent_t pool_early = nullptr;  // recorded on the compute stream once rows 0 .. L-1 of `pooled` are final
+    bool pool_early_recorded = false;
+    cudaEvent_t fence = nullptr;
+  } pipe;
+  cudaStream_t copy_stream = nullptr;
+  int opt_host_pipeline = 1;
   // Small host-entry batches are launch-latency bound (about 210 kernels per WavLM-Large forward): the second
   // identical call (same model path, batch, pitch and lengths — the reference's per-clip loop over equal-length
   // clips) is captured into a CUDA graph and replayed from then on.
@@ -201,6 +215,11 @@ struct ssr_engine {
       if (ev) cudaEventDestroy(ev);
     if (len_ring) cudaFreeHost(len_ring);
     if (last_done) cudaEventDestroy(last_done);
+    for (cudaEvent_t ev : pipe.h2d_done)
+      if (ev) cudaEventDestroy(ev);
+    if (pipe.pool_early) cudaEventDestroy(pipe.pool_early);
+    if (pipe.fence) cudaEventDestroy(pipe.fence);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (host_fence) cudaEventDestroy(host_fence);
     if (host_stream) cudaStreamDestroy(host_stream);
     for (void* p : owned) cudaFree(p);
@@ -845,6 +864,10 @@ int run_layers(ssr_engine* e, int B, int slot, bool pre_ln, bool wavlm, float* p
         if (launch_pool_finalize(part_layers, B, slot, D, lens, pooled + D, (long long)L1 * D, st, err, L - 1,
                                  (long long)part_stride, (long long)D))
           return -1;
+        if (e->pipe.active && e->pipe.pool_early) {  // rows 0 .. L-1 of `pooled` are final: their D2H may start
+          CK(cudaEventRecord(e->pipe.pool_early, st));
+          e->pipe.pool_early_recorded = true;
+        }
       }
     } else {
       // post-LN (WavLM Base+)
@@ -1049,36 +1072,37 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
   if (e->gate.ensure((size_t)M * H * 4, st, err)) return -1;
   if (e->pool_part.ensure((size_t)ceil_div(M, 32) * 2 * D * 4, st, err)) return -1;
 
-  // 1. waveform normalisation + conv0 (+ norm + GELU)
-  {
+  // 1. waveform normalisation + conv0 (+ norm + GELU), 2. conv layers 1..6 as implicit GEMMs over the channels-last
+  // signal. With the host pipeline active (run_host, LayerNorm variant) conv0 and conv1 — the two big ones — run
+  // chunk by chunk as the chunks' host-to-device copies land; the small tail layers run once over the whole batch.
+  const bool ln = d.feat_norm == SSR_FEAT_NORM_LAYER;
+  const bool fused_ln = ln && e->opt_conv_ln_fused && !e->opt_simt;
+  const bool piped = e->pipe.active && fused_ln && e->pipe.n_chunks > 1;
+  auto conv0_range = [&](int c0, int c1) -> int {
     Conv0Args a;
     memset(&a, 0, sizeof(a));
-    a.audio = audio;
+    a.audio = audio + (long long)c0 * audio_ld;
     a.audio_ld = audio_ld;
-    a.n_samples = e->nsamp_dev.as<int>();
-    a.B = B;
+    a.n_samples = e->nsamp_dev.as<int>() + c0;
+    a.B = c1 - c0;
     a.do_normalize = d.do_normalize;
-    a.stats = e->stats.as<float>();
+    a.stats = e->stats.as<float>() + 2 * c0;
     a.w = e->c0_w;
     a.wstat = e->c0_wstat;
     a.gamma = e->cln_g[0];
     a.beta = e->cln_b[0];
-    a.mode = d.feat_norm == SSR_FEAT_NORM_LAYER ? 0 : 1;
-    a.gn_acc = e->gn_acc.as<double>();
-    a.out = e->conv[0].as<bf16>();
+    a.mode = ln ? 0 : 1;
+    a.gn_acc = e->gn_acc.as<double>() + (ln ? 0 : (long long)1024 * c0);
+    a.out = e->conv[0].as<bf16>() + (long long)c0 * slots[0] * 512;
     a.slot0 = slots[0];
     e->launches += a.mode == 0 ? 2 : 4;
-    {
-      ProfScope ps(e, st, "wavlm_conv0", 2.0 * 10 * 512 * (double)B * slots[0]);
-      if (launch_wavlm_conv0(a, st, err)) return -1;
-    }
-    reg_dbg(e, "conv0", e->conv[0].p, 1, B, slots[0], 512);
-  }
-  // 2. conv layers 1..6 as implicit GEMMs over the channels-last signal
-  for (int i = 1; i < 7; ++i) {
-    const int Mi = B * slots[i];
+    ProfScope ps(e, st, "wavlm_conv0", 2.0 * 10 * 512 * (double)(c1 - c0) * slots[0]);
+    return launch_wavlm_conv0(a, st, err);
+  };
+  auto conv_range = [&](int i, int c0, int c1) -> int {
+    const int Mi = (c1 - c0) * slots[i];
     GemmOp op;
-    op.A = e->conv[i - 1].as<bf16>();
+    op.A = e->conv[i - 1].as<bf16>() + (long long)c0 * slots[i - 1] * 512;
     op.lda = (long long)ss[i] * 512;
     op.a_rows = Mi;
     op.W = e->conv_w[i];
@@ -1087,24 +1111,19 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     op.K = ks[i] * 512;
     op.a_mode = 0;
     op.a_cols = 0;
-    const bool ln = d.feat_norm == SSR_FEAT_NORM_LAYER;
-    if (ln && e->opt_conv_ln_fused && !e->opt_simt) {
+    bf16* out = e->conv[i].as<bf16>() + (long long)c0 * slots[i] * 512;
+    if (fused_ln) {
       e->launches++;
       ProfScope ps(e, st, "gemm_conv_ln", 2.0 * (double)Mi * 512.0 * (double)op.K);
-      if (launch_gemm_ln(op.A, op.lda, op.a_rows, op.W, Mi, op.K, e->cln_g[i], e->cln_b[i], 1e-5f,
-                         e->conv[i].as<bf16>(), st, e->num_sms, err))
-        return -1;
-      char nm[16];
-      snprintf(nm, sizeof nm, "conv%d", i);
-      reg_dbg(e, nm, e->conv[i].p, 1, B, slots[i], 512);
-      continue;
+      return launch_gemm_ln(op.A, op.lda, op.a_rows, op.W, Mi, op.K, e->cln_g[i], e->cln_b[i], 1e-5f, out, st,
+                            e->num_sms, err);
     }
-    op.epi = epi_plain(nullptr, ln ? ACT_NONE : ACT_GELU, nullptr, 0, nullptr, 0, e->conv[i].as<bf16>(), 512);
+    op.epi = epi_plain(nullptr, ln ? ACT_NONE : ACT_GELU, nullptr, 0, nullptr, 0, out, 512);
     if (run_gemm(e, op, st, "gemm_conv")) return -1;
     if (ln) {
       LayerNormArgs a;
       memset(&a, 0, sizeof(a));
-      a.in_bf16 = e->conv[i].as<bf16>();
+      a.in_bf16 = out;
       a.rows = Mi;
       a.D = 512;
       a.ld_in = 512;
@@ -1112,10 +1131,31 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
       a.beta = e->cln_b[i];
       a.eps = 1e-5f;
       a.gelu = 1;
-      a.out_bf16 = e->conv[i].as<bf16>();
+      a.out_bf16 = out;
       a.ld_out16 = 512;
       if (run_ln(e, a, st)) return -1;
     }
+    return 0;
+  };
+  int first_full_layer = 1;
+  if (piped) {
+    for (int c = 0; c < e->pipe.n_chunks; ++c) {
+      const int c0 = c * e->pipe.chunk_clips, c1 = std::min(B, c0 + e->pipe.chunk_clips);
+      if (c0 >= c1) break;
+      CK(cudaStreamWaitEvent(st, e->pipe.h2d_done[c], 0));
+      if (conv0_range(c0, c1)) return -1;
+      if (conv_range(1, c0, c1)) return -1;
+    }
+    first_full_layer = 2;
+  } else {
+    if (e->pipe.active)  // pipeline requested but not applicable to this model variant: wait for every chunk
+      for (int c = 0; c < e->pipe.n_chunks; ++c) CK(cudaStreamWaitEvent(st, e->pipe.h2d_done[c], 0));
+    if (conv0_range(0, B)) return -1;
+  }
+  reg_dbg(e, "conv0", e->conv[0].p, 1, B, slots[0], 512);
+  for (int i = first_full_layer; i < 7; ++i)
+    if (conv_range(i, 0, B)) return -1;
+  for (int i = 1; i < 7; ++i) {
     char nm[16];
     snprintf(nm, sizeof nm, "conv%d", i);
     reg_dbg(e, nm, e->conv[i].p, 1, B, slots[i], 512);
@@ -1545,6 +1585,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_conv_ln_fused = value;
   else if (k == "logmel_dense")
     e->opt_logmel_dense = value;
+  else if (k == "host_pipeline")
+    e->opt_host_pipeline = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;
@@ -1698,10 +1740,65 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
   cudaStream_t st = nullptr;
   if (host_entry_stream(e, &st)) return -1;
   if (forward_enter(e, st)) return -1;
+  const int L1 = e->d.layers + 1, D = e->d.hidden;
   const size_t in_bytes = (size_t)B * audio_ld * 4;
-  const size_t out_bytes = (size_t)B * (e->d.layers + 1) * e->d.hidden * 4;
+  const size_t out_bytes = (size_t)B * L1 * D * 4;
   if (e->audio_stage.ensure(in_bytes, st, err)) return -1;
   if (e->pooled_stage.ensure(out_bytes, st, err)) return -1;
+  // Large batches: chunked H2D on a copy stream overlapping the front end, early D2H of the pooled rows (HostPipe).
+  const bool pipe_ok = e->opt_host_pipeline && B >= 64 && !e->opt_profile && e->opt_snapshot_layer < 0;
+  ssr_engine::HostPipe& hp = e->pipe;
+  if (pipe_ok) {
+    if (!e->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+      for (cudaEvent_t& ev : hp.h2d_done) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&hp.pool_early, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&hp.fence, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = e->copy_stream;
+    // the copy stream starts after everything the compute stream has been made to wait for (previous forward,
+    // workspace growth)
+    CK(cudaEventRecord(hp.fence, st));
+    CK(cudaStreamWaitEvent(cs, hp.fence, 0));
+    hp.n_chunks = wavlm ? 4 : 1;
+    hp.chunk_clips = (B + hp.n_chunks - 1) / hp.n_chunks;
+    for (int c = 0; c < hp.n_chunks; ++c) {
+      const int c0 = c * hp.chunk_clips, c1 = std::min((int)B, c0 + hp.chunk_clips);
+      if (c0 < c1)
+        CK(cudaMemcpyAsync(e->audio_stage.as<float>() + (size_t)c0 * audio_ld, audio_host + (size_t)c0 * audio_ld,
+                           (size_t)(c1 - c0) * audio_ld * 4, cudaMemcpyHostToDevice, cs));
+      CK(cudaEventRecord(hp.h2d_done[c], cs));
+    }
+    hp.active = true;
+    hp.pool_early_recorded = false;
+    int rc;
+    if (wavlm) {
+      rc = wavlm_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B, e->pooled_stage.as<float>(), st);
+    } else {
+      CK(cudaStreamWaitEvent(st, hp.h2d_done[0], 0));
+      rc = whisper_forward(e, e->audio_stage.as<float>(), audio_ld, n_samples, B, e->pooled_stage.as<float>(), st);
+    }
+    hp.active = false;
+    if (rc) {
+      cudaStreamSynchronize(cs);
+      return rc;
+    }
+    const size_t pitch = (size_t)L1 * D * 4;
+    if (hp.pool_early_recorded) {
+      CK(cudaStreamWaitEvent(cs, hp.pool_early, 0));
+      CK(cudaMemcpy2DAsync(pooled_host, pitch, e->pooled_stage.p, pitch, (size_t)(L1 - 1) * D * 4, (size_t)B,
+                           cudaMemcpyDeviceToHost, cs));
+      CK(cudaMemcpy2DAsync(pooled_host + (size_t)(L1 - 1) * D, pitch, e->pooled_stage.as<float>() + (size_t)(L1 - 1) * D,
+                           pitch, (size_t)D * 4, (size_t)B, cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(hp.fence, cs));
+      CK(cudaStreamWaitEvent(st, hp.fence, 0));
+    } else {
+      CK(cudaMemcpyAsync(pooled_host, e->pooled_stage.p, out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    if (forward_leave(e, st)) return -1;
+    CK(cudaStreamSynchronize(st));
+    return 0;
+  }
   CK(cudaMemcpyAsync(e->audio_stage.p, audio_host, in_bytes, cudaMemcpyHostToDevice, st));
   int rc = forward_graphed(e, wavlm ? 0 : 1, e->audio_stage.as<float>(), audio_ld, n_samples, B,
                            e->pooled_stage.as<float>(), nullptr, st);

@@ -591,6 +591,34 @@ def test_device_relbias_table_is_the_hf_bucket_gather():
             assert int(bucket[r + R - 1]) in hit.tolist(), r
 
 
+def test_host_pipeline_is_bit_identical_to_plain_copies():
+    """Batches of >= 64 clips through the *_host entry points take the pipelined path (chunked H2D overlapping conv0 /
+    conv1, early D2H of hidden_states[0 .. L-1]); results must equal the plain copy-run-copy path bit for bit, for
+    ragged batches whose size is not a multiple of the chunk count, for both model families and for the post-LN
+    variant (no early copy)."""
+    from ssr_b200 import synth
+
+    rng = np.random.default_rng(11)
+    for name in ("tiny_stable", "tiny_post"):
+        _, _, eng = wavlm(name)
+        clips = [synth.clip_by_index(300 + i, int(rng.integers(4000, 20000))) for i in range(70)]
+        eng.set_option("host_pipeline", 0)
+        want = eng.pooled(clips)
+        eng.set_option("host_pipeline", 1)
+        np.testing.assert_array_equal(eng.pooled(clips), want)
+        np.testing.assert_allclose(eng.pooled(clips[:64]), want[:64], rtol=0, atol=2e-6 * np.abs(want).max())
+        # interleave a small (graph-eligible) call and a second big one: the copy stream must not race the next forward
+        one = eng.pooled([clips[0]])
+        np.testing.assert_array_equal(eng.pooled(clips), want)
+        np.testing.assert_array_equal(eng.pooled([clips[0]]), one)
+    _, _, weng = whisper("tiny")
+    wclips = [synth.clip_by_index(400 + i, int(rng.integers(2000, 30000))) for i in range(64)]
+    weng.set_option("host_pipeline", 0)
+    wwant = weng.pooled(wclips)
+    weng.set_option("host_pipeline", 1)
+    np.testing.assert_array_equal(weng.pooled(wclips), wwant)
+
+
 def test_single_row_views_with_degenerate_stride():
     """`x[None]` of a 1-D array has stride 0 in its size-1 dimension; the shim must still hand the C ABI a row pitch."""
     import torch
