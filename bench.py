@@ -429,6 +429,8 @@ def main():
                     help="N > 1: all-gather on a side stream overlapping the next step (default) or on the compute stream")
     ap.add_argument("--sustain", type=float, default=5.0, help="seconds of the back-to-back sustained loop (0 = skip)")
     ap.add_argument("--ref-clips", type=int, default=8, help="--impl reference: clips per step")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
+                    help="A/B measurements: process-wide kernel knob passed to ssr_tuning_set (e.g. pdl=0)")
     args = ap.parse_args()
     rank, local, world = dist_env()
     if world != args.gpus and world > 1:
@@ -454,6 +456,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     peaks = load_peaks()
+    for kv in args.tune:
+        from ssr_b200 import _lib
+
+        key, _, val = kv.partition("=")
+        if _lib.load().ssr_tuning_set(key.encode(), int(val)) != 0:
+            raise SystemExit(f"unknown tuning knob {key!r}")
     side_legs = rank == 0 and world == 1  # CPU / library baselines and parity: N = 1 only
 
     # ---- headline: WavLM-Large, B clips of 3 s per GPU (BASELINE.json configs[1]) ----
@@ -483,6 +491,8 @@ def main():
                                         "a length upload through the pinned ring every step"},
         "gpu_launches": int(r["launches"]),
     }
+    if args.tune:
+        line["tuning"] = args.tune
     if args.sustain > 0:
         line["sustained_value"] = round(world * B * r["sustained_steps"] / r["sustained_s"], 1)
         line["sustained"] = {"seconds": round(r["sustained_s"], 2), "steps": r["sustained_steps"],

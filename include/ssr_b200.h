@@ -122,7 +122,9 @@ int32_t ssr_wavlm_rel_bucket(int32_t rel);
  * the variant they captured until the graph is dropped). Keys: "attention_variant" (bit 0: packed fp32 pair arithmetic
  * in the softmax; bit 1: a quarter of the exponentials on the FMA pipe; the default, 1, is the fastest measured),
  * "attention_paired" (1, default: clips of two query tiles are walked so that both tiles of a (clip, head) run at the
- * same time on neighbouring CTAs and K / V are read from HBM once; 0: query-tile-major order). Returns 0, or -1 for an unknown key. */
+ * same time on neighbouring CTAs and K / V are read from HBM once; 0: query-tile-major order), "pdl" (1: the per-layer kernels
+ * are launched with programmatic stream serialization so that a kernel's prologue overlaps its predecessor's tail;
+ * 0, default: plain stream order — measured faster). Returns 0, or -1 for an unknown key. */
 int ssr_tuning_set(const char* key, int32_t value);
 /* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t ssr_launch_count(const ssr_engine* e);

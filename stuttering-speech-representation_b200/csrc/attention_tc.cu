@@ -342,6 +342,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  griddep_wait();  // programmatic dependent launch: qkv / gate / lens come from earlier kernels
+  griddep_launch();
 
   if (threadIdx.x == 128) {
     // ============================ TMA producer ============================
@@ -733,7 +735,8 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   }
   const int bsel = a.gate != nullptr ? 1 : 0;
   const int var = g_attention_variant & 3;
-  kern[bsel][var]<<<grid, 192, bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st>>>(tmq, tmkv, a, (int)items, step);
+  launch_pdl(kern[bsel][var], dim3(grid), dim3(192), bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st, tmq, tmkv, a,
+             (int)items, step);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("attention_tc launch: ") + cudaGetErrorString(ce);

@@ -97,4 +97,32 @@ __device__ __forceinline__ float gelu_fast(float x) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+#ifdef __CUDACC__
+// Process-wide switch (ssr_tuning_set "pdl"): 1 = the per-layer kernels (LayerNorm, CTA-pair GEMM, attention) are
+// launched with programmatic stream serialization, so that each one's prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, CTA scheduling) overlaps the tail of its predecessor instead of following it.
+// Default 0: measured on B200 the step gets SLOWER with it (WavLM-Large 33.5 -> 34.3 ms, Whisper-large 162 -> 165 ms,
+// two alternating runs each): successor CTAs that become resident early sit in griddepcontrol.wait holding warp
+// slots, registers and TMEM that the running kernel's own CTAs then lack.
+extern int g_pdl;
+
+// Launch `kernel` (which calls ptx::griddep_wait before its first dependent global access) with the programmatic
+// dependent launch attribute. Compile-time __cluster_dims__ of the kernel are honoured by cudaLaunchKernelEx.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace ssr

@@ -26,6 +26,11 @@ using namespace ssr;
 namespace {
 
 std::string g_create_error;
+}  // namespace
+namespace ssr {
+int g_pdl = 0;
+}
+namespace {
 
 #define CK(call)                                                                                  \
   do {                                                                                            \
@@ -118,6 +123,10 @@ struct ssr_engine {
   int opt_conv_ln_fused = 1;    // 1: WavLM-Large conv layers 1-6 as conv + LayerNorm + GELU in one kernel (gemm_ln.cu)
   std::vector<ProfEntry> prof;
   std::string prof_json;
+  // Algorithmic FLOPs of the profile entries count LIVE rows: the transformer runs on `slot` rows per clip of which
+  // lens[b] are live (149 of 150 for 3 s clips). prof_rows = live rows / slot rows of the current forward, applied
+  // to the per-layer GEMMs; prof_att = sum(len^2) / (B * slot^2), applied to attention.
+  double prof_rows = 1.0, prof_att = 1.0;
 
   // ---- weights (device) ----
   std::vector<void*> owned;  // every cudaMalloc'd weight block
@@ -680,7 +689,10 @@ struct ProfScope {
 
 int run_gemm(ssr_engine* e, const GemmOp& op, cudaStream_t st, const char* name = "gemm") {
   e->launches += e->opt_simt ? (op.epi.pool_part ? 2 : 1) : 1;
-  ProfScope ps(e, st, name, 2.0 * (double)op.M * (double)op.N * (double)op.K);
+  const bool layer_gemm = name[0] == 'g' && (!strcmp(name, "gemm_qkv") || !strcmp(name, "gemm_out") ||
+                                              !strcmp(name, "gemm_ffn1") || !strcmp(name, "gemm_ffn2") ||
+                                              !strcmp(name, "gemm_proj"));
+  ProfScope ps(e, st, name, 2.0 * (double)op.M * (double)op.N * (double)op.K * (layer_gemm ? e->prof_rows : 1.0));
   return launch_gemm(op, st, e->opt_simt != 0, e->num_sms, e->err);
 }
 
@@ -691,8 +703,8 @@ int run_ln(ssr_engine* e, const LayerNormArgs& a, cudaStream_t st) {
 }
 int run_attn(ssr_engine* e, const AttentionArgs& a, cudaStream_t st) {
   e->launches++;
-  // QK^T and PV: 2 * 2 * T^2 * 64 per head (T = slot; masked keys are still multiplied)
-  ProfScope ps(e, st, "attention", 4.0 * (double)a.B * a.H * (double)a.slot * a.slot * 64.0);
+  // QK^T and PV: 2 * 2 * T^2 * 64 per head, T = the clip's live frames
+  ProfScope ps(e, st, "attention", 4.0 * (double)a.B * a.H * (double)a.slot * a.slot * 64.0 * e->prof_att);
   return e->opt_attn_simt ? launch_attention(a, st, e->err) : launch_attention_tc(a, st, e->err);
 }
 
@@ -1050,6 +1062,15 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
     return -1;
   }
   const int M = (int)Mll;
+  {
+    double live = 0.0, live2 = 0.0;
+    for (int b = 0; b < B; ++b) {
+      live += lens[b];
+      live2 += (double)lens[b] * lens[b];
+    }
+    e->prof_rows = live / ((double)B * slot);
+    e->prof_att = live2 / ((double)B * slot * slot);
+  }
   if (upload_lengths(e, n_samples, B, lens, st)) return -1;
   if (build_relbias(e, slot, st, err)) return -1;
 
@@ -1422,6 +1443,7 @@ int whisper_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const i
     return -1;
   }
   if (whisper_logmel(e, audio, audio_ld, n_samples, B, nullptr, true, st)) return -1;
+  e->prof_rows = e->prof_att = 1.0;
   const int M = B * 1500;
   if (e->c1.ensure(((size_t)B * 3002 + 8) * D * 2, st, err)) return -1;
   if (e->h.ensure((size_t)M * D * 4, st, err)) return -1;
@@ -1760,7 +1782,7 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
     // workspace growth)
     CK(cudaEventRecord(hp.fence, st));
     CK(cudaStreamWaitEvent(cs, hp.fence, 0));
-    hp.n_chunks = wavlm ? 4 : 1;
+    hp.n_chunks = wavlm ? 8 : 1;
     hp.chunk_clips = (B + hp.n_chunks - 1) / hp.n_chunks;
     for (int c = 0; c < hp.n_chunks; ++c) {
       const int c0 = c * hp.chunk_clips, c1 = std::min((int)B, c0 + hp.chunk_clips);
@@ -1901,6 +1923,10 @@ int ssr_tuning_set(const char* key, int32_t value) {
   const std::string k(key);
   if (k == "attention_variant") {
     g_attention_variant = value & 3;
+    return 0;
+  }
+  if (k == "pdl") {
+    g_pdl = value != 0;
     return 0;
   }
   if (k == "attention_paired") {

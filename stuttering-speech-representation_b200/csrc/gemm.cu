@@ -434,6 +434,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above is independent of earlier kernels; from here on activations / residuals of the predecessor are
+  // read and its inputs may be overwritten (programmatic dependent launch, see ptx.cuh).
+  griddep_wait();
+  griddep_launch();
 
   if (threadIdx.x == EPI_WARPS2 * 32) {
     // ===================== TMA producer (both CTAs; bytes are credited to the leader's barrier) =================
@@ -884,8 +888,8 @@ static int launch_tc2(const GemmOp& op, GemmParams& p, cudaStream_t stream, int 
   const int total = p.num_m_tiles * p.num_n_tiles;
   const int max_clusters = num_sms / 2;
   const int grid = 2 * (total < max_clusters ? total : max_clusters);
-  gemm_tc2_kernel<<<grid, TC2_THREADS, TC2_SMEM_BYTES, stream>>>(tmA, tmB, p);
-  cudaError_t ce = cudaGetLastError();
+  cudaError_t ce = launch_pdl(gemm_tc2_kernel, dim3(grid), dim3(TC2_THREADS), TC2_SMEM_BYTES, stream, tmA, tmB, p);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("gemm_tc2_kernel launch: ") + cudaGetErrorString(ce);
     return -1;

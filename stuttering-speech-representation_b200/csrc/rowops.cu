@@ -4,6 +4,7 @@
 // 314-373,513; gate HF/models/wavlm/modeling_wavlm.py:167-180; pool REF/WavLM_embeddings.py:321,
 // REF/whisper_embeddings_large.py:278.
 #include "common.cuh"
+#include "ptx.cuh"
 #include "kernels.cuh"
 
 namespace ssr {
@@ -22,6 +23,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const LayerNormArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
+  ptx::griddep_wait();    // programmatic dependent launch: the rows come from the previous kernel
+  ptx::griddep_launch();
   if (row >= a.rows) return;
   constexpr int D = NV * 128;
   float v[NV][4];
@@ -132,9 +135,9 @@ int launch_layernorm(const LayerNormArgs& a, cudaStream_t st, std::string& err) 
 #define SSR_LN_CASE(NV)                                                   \
   case NV * 128:                                                          \
     if (bf)                                                               \
-      layernorm_kernel<NV, true><<<grid, 256, 0, st>>>(a);                \
+      launch_pdl(layernorm_kernel<NV, true>, dim3(grid), dim3(256), 0, st, a);  \
     else                                                                  \
-      layernorm_kernel<NV, false><<<grid, 256, 0, st>>>(a);               \
+      launch_pdl(layernorm_kernel<NV, false>, dim3(grid), dim3(256), 0, st, a); \
     break;
   switch (a.D) {
     SSR_LN_CASE(2)
