@@ -677,451 +677,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
 
 
-// ============================================================================================ 128-key blocks, P in TMEM
-// Same roles and item walk as attention_tc_kernel, but
-//   * a key block is 128 keys: every fixed latency of a block (barrier wake-up, tcgen05.ld round trip, arrive, the
-//     tensor-core round trip to the next S) is paid once per 128 keys instead of once per 64. With 64-key blocks a
-//     softmax warp spends ~0.5 k cycles of a ~1.9 k cycle block on the MUFU unit and two warps share a scheduler:
-//     the unit that bounds attention at head_dim 64 (16 ex2 / clk / SM, twice the tensor-core time) is 58 % busy
-//     (profiles/r02_attention_whisper.md). Twice the work per round trip is what closes that gap.
-//   * P never touches shared memory: the softmax warps write it (bf16 pairs, tcgen05.st) into tensor memory and
-//     P V is issued with the A operand in TMEM. No 128-bit STS, no XOR swizzle arithmetic, no generic->async proxy
-//     fence per block; the freed shared memory holds 128-key K / V stages.
-//   * TMEM (256 columns per CTA, two CTAs per SM): S [0,128) single-buffered, O [128,192), P [192,256). One S buffer
-//     means S of block n+1 is issued when the softmax of block n is done (its bar_p arrival); the tensor-core round
-//     trip that follows is covered by the other resident CTA, exactly like FA4's two-tile ping-pong. S_{n+1} goes to
-//     the tensor pipe BEFORE P_n V_n (the softmax warps are waiting for S, nobody is waiting for O), so a softmax
-//     warp waits for bar_o of block n-1 before it overwrites P (normally long complete).
-//   * block 0 of an item takes its exact row maximum in a first pass over TMEM and re-reads S for the exponentials
-//     (128 scores per row do not fit in registers next to everything else); later blocks are one pass.
-//   * K and V have separate 2-stage rings: K of block n is free once S_n has retired, V only after P_n V_n.
-constexpr int KB2 = 128;                      // keys per block
-constexpr int KV2_BYTES = KB2 * 64 * 2;       // [128 x 64] bf16
-constexpr int S2_Q = 0;
-constexpr int S2_K = Q_BYTES;                 // 2 stages
-constexpr int S2_V = S2_K + 2 * KV2_BYTES;    // 2 stages
-constexpr int S2_STAGE = S2_V + 2 * KV2_BYTES;  // epilogue transposition, [128 x 64] bf16
-constexpr int S2_BAR = S2_STAGE + Q_BYTES;
-constexpr int S2_LEN = S2_BAR + 192;
-constexpr int WIN2 = 160;                     // bias window per softmax warp and block: 128 keys + 31 rows of skew (+1)
-constexpr int S2_WIN = S2_BAR + 256;
-template <bool HAS_BIAS>
-struct Lay2 {
-  static constexpr int SM_GATE = S2_WIN + (HAS_BIAS ? 4 * WIN2 * 4 : 0);
-  static constexpr int SMEM = SM_GATE + (HAS_BIAS ? 2 * 128 * 4 : 0);
-  static_assert(2 * (SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
-};
-constexpr int T2_S = 0, T2_O = 128, T2_P = 192;
-
-// One 32-key chunk: scores -> (bias, mask) -> running maximum and / or probabilities (bf16 pairs in pk[16]).
-template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX, bool POLY, bool PACK2>
-__device__ __forceinline__ void chunk2(const uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel,
-                                       float mu2, float& m_blk, float& l_blk, uint32_t (&pk)[16]) {
-  uint64_t l2 = 0;
-  const uint64_t scale2 = pack2(LOG2E, LOG2E), shift2 = pack2(-mu2, -mu2), gate2 = pack2(gate, gate);
-#pragma unroll
-  for (int k = 0; k < 32; k += 2) {
-    float v0 = __uint_as_float(raw[k]), v1 = __uint_as_float(raw[k + 1]);
-    if (HAS_BIAS) {
-      if (PACK2) {
-        unpack2(fma2(gate2, pack2(rel[k], rel[k + 1]), pack2(v0, v1)), v0, v1);
-      } else {
-        v0 = fmaf(gate, rel[k], v0);
-        v1 = fmaf(gate, rel[k + 1], v1);
-      }
-    }
-    if (MASK) {
-      if (jg0 + k >= len) v0 = -INFINITY;
-      if (jg0 + k + 1 >= len) v1 = -INFINITY;
-    }
-    if (TRACK_MAX) m_blk = fmaxf(m_blk, fmaxf(v0, v1));
-    if (WRITE_P) {
-      const bool poly = POLY && (k & 6) == 0;
-      float x0, x1;
-      if (PACK2) {
-        unpack2(fma2(pack2(v0, v1), scale2, shift2), x0, x1);
-      } else {
-        x0 = fmaf(v0, LOG2E, -mu2);
-        x1 = fmaf(v1, LOG2E, -mu2);
-      }
-      const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
-      const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
-      if (PACK2)
-        l2 = add2(l2, pack2(p0, p1));
-      else
-        l_blk += p0 + p1;
-      __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);  // low half = even key: the TMEM A-operand packing
-      pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-    }
-  }
-  if (WRITE_P && PACK2) {
-    float la, lb;
-    unpack2(l2, la, lb);
-    l_blk += la + lb;
-  }
-}
-
-template <bool HAS_BIAS, int VAR>
-__global__ void __launch_bounds__(192, 2)
-attention_tc128_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
-                       const AttentionArgs a, const int n_items, const Step step) {
-  constexpr bool PACK2 = (VAR & 1) != 0, POLY = (VAR & 2) != 0;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S2_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* bar_s = bars + 10;    // one S buffer: phase = block parity
-  uint64_t* bar_p = bars + 11;
-  uint64_t* bar_o = bars + 12;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023) __trap();
-    prefetch_tmap(&tmq);
-    prefetch_tmap(&tmkv);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&bar_o[i], 1);
-    }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    fence_mbar_init();
-  }
-  if (warp == 5) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  if (HAS_BIAS && threadIdx.x < 128) {
-    float* g0 = reinterpret_cast<float*>(smem + Lay2<HAS_BIAS>::SM_GATE);
-    g0[threadIdx.x] = 0.f;
-    g0[128 + threadIdx.x] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  griddep_wait();
-  griddep_launch();
-
-  if (threadIdx.x == 128) {
-    // ============================ TMA producer ============================
-    uint32_t n_item = 0, n = 0;
-    Cursor cur;
-    cur.init(a, step);
-    int* lsm = reinterpret_cast<int*>(smem + S2_LEN) + 8;
-    uint32_t lbuf = 0;
-    ItemPre nxt = cur.load(a, lsm);
-    cp_async_commit();
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
-      cp_async_wait_all();
-      const Item it = finish_item(a, nxt, lsm[lbuf]);
-      if (idx + (int)gridDim.x < n_items) {
-        cur.advance(a, step);
-        nxt = cur.load(a, lsm + (lbuf ^ 1));
-        cp_async_commit();
-      }
-      if (!it.valid) continue;
-      const int row0 = it.b * a.slot;
-      const int nkb = (it.len + KB2 - 1) / KB2;
-      mbar_wait(q_empty, (n_item & 1) ^ 1);
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(smem + S2_Q, &tmq, q_full, it.h * HD, row0 + it.q0);
-      for (int j = 0; j < nkb; ++j, ++n) {
-        const int s = n & 1;
-        const uint32_t ph = ((n >> 1) & 1) ^ 1;
-        mbar_wait(&k_empty[s], ph);
-        mbar_arrive_expect_tx(&k_full[s], KV2_BYTES);
-        tma_load_2d(smem + S2_K + s * KV2_BYTES, &tmkv, &k_full[s], a.D + it.h * HD, row0 + j * KB2);
-        mbar_wait(&v_empty[s], ph);
-        mbar_arrive_expect_tx(&v_full[s], KV2_BYTES);
-        tma_load_2d(smem + S2_V + s * KV2_BYTES, &tmkv, &v_full[s], 2 * a.D + it.h * HD, row0 + j * KB2);
-      }
-      ++n_item;
-    }
-  } else if (threadIdx.x == 160) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
-    const uint64_t dq = umma_desc_sw128(smem_u32(smem + S2_Q));
-    uint32_t n_item = 0, n = 0;
-    bool have_prev = false, prev_first = false;
-    int prev_n16 = 0;
-    // P_{n-1} V_{n-1}: A = P in tensor memory (8 columns per 16 keys), B = V_{n-1} (MN-major, 2048 B per 16 keys)
-    auto issue_pv_prev = [&]() {
-      const uint32_t pn = n - 1;
-      const int ps = pn & 1;
-      mbar_wait(&v_full[ps], (pn >> 1) & 1);
-      tc_fence_after();
-      const uint64_t dv = umma_desc_sw128_mn(smem_u32(smem + S2_V + ps * KV2_BYTES));
-      for (int k = 0; k < prev_n16; ++k)
-        umma_bf16_ts(tmem + T2_O, tmem + T2_P + 8 * k, dv + (uint64_t)(k * 2048 >> 4), idesc_pv,
-                     (!prev_first || k != 0) ? 1u : 0u);
-      umma_commit(&v_empty[ps]);
-      umma_commit(&bar_o[pn & 1]);
-    };
-    Cursor cur;
-    cur.init(a, step);
-    int* lsm = reinterpret_cast<int*>(smem + S2_LEN) + 10;
-    uint32_t lbuf = 0;
-    ItemPre nxt = cur.load(a, lsm);
-    cp_async_commit();
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
-      cp_async_wait_all();
-      const Item it = finish_item(a, nxt, lsm[lbuf]);
-      if (idx + (int)gridDim.x < n_items) {
-        cur.advance(a, step);
-        nxt = cur.load(a, lsm + (lbuf ^ 1));
-        cp_async_commit();
-      }
-      if (!it.valid) continue;
-      const int nkb = (it.len + KB2 - 1) / KB2;
-      mbar_wait(q_full, n_item & 1);
-      for (int j = 0; j < nkb; ++j) {
-        const int s = n & 1;
-        const int nlive = min(KB2, it.len - j * KB2);
-        const int n16 = (nlive + 15) >> 4;
-        mbar_wait(&k_full[s], (n >> 1) & 1);
-        // the single S buffer and the single P buffer are free once the softmax of the previous block has arrived
-        if (have_prev) mbar_wait(bar_p, (n - 1) & 1);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(smem + S2_K + s * KV2_BYTES));
-        const uint32_t idesc_s = umma_idesc_bf16(128, n16 * 16);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T2_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        if (j == nkb - 1) umma_commit(q_empty);
-        umma_commit(&k_empty[s]);
-        umma_commit(bar_s);
-        if (have_prev) issue_pv_prev();
-        have_prev = true;
-        prev_n16 = n16;
-        prev_first = (j == 0);
-        ++n;
-      }
-      mbar_wait(bar_p, (n - 1) & 1);
-      tc_fence_after();
-      issue_pv_prev();
-      have_prev = false;
-      ++n_item;
-    }
-  } else if (warp < 4) {
-    // ============================ softmax / output warps ============================
-    const uint32_t quad = warp;
-    const int il = quad * 32 + lane;
-    const uint32_t lane_addr = (quad * 32u) << 16;
-    uint32_t n = 0;
-    Cursor cur;
-    cur.init(a, step);
-    int* lsm = reinterpret_cast<int*>(smem + S2_LEN) + quad * 2;
-    ItemPre nxt = cur.load(a, lsm, lane == 0);
-    float* gsm = reinterpret_cast<float*>(smem + Lay2<HAS_BIAS>::SM_GATE) + il;
-    uint32_t gbuf = 0;
-    auto prefetch_gate = [&](const ItemPre& p, uint32_t buf) {
-      if (HAS_BIAS && p.q0 + il < a.slot)
-        cp_async_f32(gsm + buf * 128, a.gate + ((long long)p.b * a.slot + p.q0 + il) * a.H + p.h);
-      cp_async_commit();
-    };
-    prefetch_gate(nxt, 0);
-    float* win = reinterpret_cast<float*>(smem + S2_WIN) + quad * WIN2;
-    const float* rel = win + 31 - lane;
-    const uint32_t ts = tmem + lane_addr + T2_S, tp = tmem + lane_addr + T2_P, to = tmem + lane_addr + T2_O;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, gbuf ^= 1) {
-      cp_async_wait_all();
-      __syncwarp();
-      const Item it = finish_item(a, nxt, lsm[gbuf]);
-      float gate = 0.f;
-      if (HAS_BIAS) gate = gsm[gbuf * 128];
-      if (idx + (int)gridDim.x < n_items) {
-        cur.advance(a, step);
-        nxt = cur.load(a, lsm + (gbuf ^ 1), lane == 0);
-        prefetch_gate(nxt, gbuf ^ 1);
-      }
-      if (!it.valid) continue;
-      const int row0 = it.b * a.slot;
-      const bool warp_live = it.q0 + (int)quad * 32 < it.len;
-      const int nkb = (it.len + KB2 - 1) / KB2;
-      const float* table = nullptr;
-      int win_base = 0;
-      if (HAS_BIAS) {
-        table = a.relbias + (long long)it.h * a.rel_stride;
-        win_base = a.rel_center - 31 - (it.q0 + (int)quad * 32);
-      }
-      constexpr float L_SAFE = 1.8446744e19f * 64.0f;  // 2^70
-      float m_ref = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < nkb; ++j, ++n) {
-        const int k0 = j * KB2;
-        const int nlive = min(KB2, it.len - k0);
-        const int nch = (nlive + 31) >> 5;
-        const bool need_mask = (nlive & 31) != 0;
-        float w[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        if (HAS_BIAS && warp_live) {
-          const int t0 = win_base + k0 + (int)lane, hi = a.rel_stride - 1;
-#pragma unroll
-          for (int t = 0; t < 5; ++t) w[t] = __ldg(table + min(max(t0 + 32 * t, 0), hi));
-        }
-        mbar_wait(bar_s, n & 1);
-        __syncwarp();  // also: every lane is done reading the previous block's window
-        tc_fence_after();
-        if (warp_live) {
-          if (HAS_BIAS) {
-#pragma unroll
-            for (int t = 0; t < 5; ++t) win[lane + 32 * t] = w[t];
-            __syncwarp();
-          }
-          uint32_t ra[32], rb[32], pk[16];
-          float dummy = 0.f;
-          if (j == 0) {
-            // pass 1 of the item's first block: exact row maximum (biased, masked scores), nothing is kept
-            float m_blk = -INFINITY;
-            tmem_ld_32x32(ts, ra);
-            for (int c = 0; c < nch; c += 2) {
-              if (c + 1 < nch) tmem_ld_32x32(ts + (c + 1) * 32, rb);
-              tmem_wait_ld();
-              if (c == nch - 1 && need_mask)
-                chunk2<HAS_BIAS, true, false, true, false, PACK2>(ra, k0 + c * 32, it.len, gate, rel + c * 32, 0.f, m_blk, dummy, pk);
-              else
-                chunk2<HAS_BIAS, false, false, true, false, PACK2>(ra, k0 + c * 32, it.len, gate, rel + c * 32, 0.f, m_blk, dummy, pk);
-              if (c + 1 < nch) {
-                if (c + 2 < nch) tmem_ld_32x32(ts + (c + 2) * 32, ra);
-                if (c + 1 == nch - 1 && need_mask)
-                  chunk2<HAS_BIAS, true, false, true, false, PACK2>(rb, k0 + (c + 1) * 32, it.len, gate, rel + (c + 1) * 32, 0.f, m_blk, dummy, pk);
-                else
-                  chunk2<HAS_BIAS, false, false, true, false, PACK2>(rb, k0 + (c + 1) * 32, it.len, gate, rel + (c + 1) * 32, 0.f, m_blk, dummy, pk);
-              }
-            }
-            m_ref = m_blk;
-          }
-          // exponentials against the item's reference maximum, 32 keys at a time, straight into tensor memory
-          auto exp_pass = [&](float mu2, float& l_blk, bool masked_everywhere) {
-            tmem_ld_32x32(ts, ra);
-            for (int c = 0; c < nch; c += 2) {
-              if (c + 1 < nch) tmem_ld_32x32(ts + (c + 1) * 32, rb);
-              tmem_wait_ld();
-              if ((c == nch - 1 && need_mask) || masked_everywhere)
-                chunk2<HAS_BIAS, true, true, false, POLY, PACK2>(ra, k0 + c * 32, it.len, gate, rel + c * 32, mu2, dummy, l_blk, pk);
-              else
-                chunk2<HAS_BIAS, false, true, false, POLY, PACK2>(ra, k0 + c * 32, it.len, gate, rel + c * 32, mu2, dummy, l_blk, pk);
-              if (c == 0 && j > 0) {
-                // P is single-buffered: P_{n-1} V_{n-1} (issued after S_n) must have retired before it is overwritten
-                mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
-                tc_fence_after();
-              }
-              tmem_st_32x16(tp + c * 16, pk);
-              if (c + 1 < nch) {
-                if (c + 2 < nch) tmem_ld_32x32(ts + (c + 2) * 32, ra);
-                if (c + 1 == nch - 1 && need_mask)
-                  chunk2<HAS_BIAS, true, true, false, POLY, PACK2>(rb, k0 + (c + 1) * 32, it.len, gate, rel + (c + 1) * 32, mu2, dummy, l_blk, pk);
-                else
-                  chunk2<HAS_BIAS, false, true, false, POLY, PACK2>(rb, k0 + (c + 1) * 32, it.len, gate, rel + (c + 1) * 32, mu2, dummy, l_blk, pk);
-                tmem_st_32x16(tp + (c + 1) * 16, pk);
-              }
-            }
-          };
-          float mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-          float l_blk = 0.f;
-          exp_pass(mu2, l_blk, false);
-          const bool unsafe = !(l_blk < L_SAFE);  // also true for NaN / inf
-          if (j > 0 && __any_sync(0xffffffffu, unsafe)) {
-            // rare: the reference of some row is too stale. Raise it to this block's exact maximum, rescale that
-            // row's O and running sum (O is stable: P_{n-1} V_{n-1} has retired, see bar_o above), redo the block.
-            float m_blk = -INFINITY;
-            tmem_ld_32x32(ts, ra);
-            for (int c = 0; c < nch; ++c) {
-              tmem_wait_ld();
-              chunk2<HAS_BIAS, true, false, true, false, PACK2>(ra, k0 + c * 32, it.len, gate, rel + c * 32, 0.f, m_blk, dummy, pk);
-              if (c + 1 < nch) tmem_ld_32x32(ts + (c + 1) * 32, ra);
-            }
-            const float m_new = unsafe ? fmaxf(m_ref, m_blk) : m_ref;
-            const float alpha = (m_new == m_ref) ? 1.f : ex2_approx((m_ref - m_new) * LOG2E);
-            m_ref = m_new;
-            mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-            l_run *= alpha;
-            tmem_wait_st();
-            tmem_ld_32x32(to, ra);
-            tmem_ld_32x32(to + 32, rb);
-            tmem_wait_ld();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              ra[k] = __float_as_uint(__uint_as_float(ra[k]) * alpha);
-              rb[k] = __float_as_uint(__uint_as_float(rb[k]) * alpha);
-            }
-            tmem_st_32x32(to, ra);
-            tmem_st_32x32(to + 32, rb);
-            tmem_wait_st();
-            l_blk = 0.f;
-            exp_pass(mu2, l_blk, true);
-          }
-          l_run += l_blk;
-          tmem_wait_st();
-        } else if (j > 0) {
-          // a warp without live rows keeps the barrier protocol going (phases of bar_o advance per block)
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-      }
-      // the one true round-trip wait per item: P V of the last block
-      mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
-      __syncwarp();
-      tc_fence_after();
-      if (warp_live) {
-        uint32_t a0[32], a1[32];
-        tmem_ld_32x32(to, a0);
-        tmem_ld_32x32(to + 32, a1);
-        tmem_wait_ld();
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-        uint8_t* stage = smem + S2_STAGE + quad * 32 * 128;
-        {
-          uint8_t* mine = stage + lane * 128;
-          const uint32_t sw = lane & 7;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            uint32_t wv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t* src = q < 4 ? a0 : a1;
-              const int c = (q & 3) * 8 + 2 * e;
-              __nv_bfloat162 b2 =
-                  __floats2bfloat162_rn(__uint_as_float(src[c]) * inv, __uint_as_float(src[c + 1]) * inv);
-              wv[e] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            *reinterpret_cast<uint4*>(mine + ((q ^ sw) * 16)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          }
-        }
-        __syncwarp();
-        {
-          const uint32_t rsub = lane >> 3, cch = lane & 7;
-          bf16* dst = a.out + ((long long)row0 + it.q0 + quad * 32) * a.D + it.h * HD + cch * 8;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint32_t r = t * 4 + rsub;
-            const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((cch ^ (r & 7)) * 16));
-            if (it.q0 + (int)(quad * 32 + r) < it.len) *reinterpret_cast<uint4*>(dst + (long long)r * a.D) = v;
-          }
-        }
-        __syncwarp();
-      }
-      tc_fence_before();  // the TMEM reads above are ordered before the bar_p arrival that lets the next item reuse O
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem, TMEM_COLS);
-  }
-}
-
 }  // namespace
 
 // Kernel variant (see attention_tc_kernel: bit 0 = packed pair arithmetic, bit 1 = polynomial exp2 share);
@@ -1129,8 +684,6 @@ attention_tc128_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_con
 int g_attention_variant = 1;
 // 1: two-tile clips use the paired item order (see Cursor); 0: query-tile-major order everywhere.
 int g_attention_paired = 1;
-// Keys per block: 128 = attention_tc128_kernel (P in tensor memory), 64 = attention_tc_kernel (P in shared memory).
-int g_attention_block = 128;
 
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err) {
   if (a.D != a.H * HD) {
@@ -1183,31 +736,8 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   }
   const int bsel = a.gate != nullptr ? 1 : 0;
   const int var = g_attention_variant & 3;
-  if (g_attention_block == 128) {
-    static const KernelFn k2[2][4] = {
-        {attention_tc128_kernel<false, 0>, attention_tc128_kernel<false, 1>, attention_tc128_kernel<false, 2>,
-         attention_tc128_kernel<false, 3>},
-        {attention_tc128_kernel<true, 0>, attention_tc128_kernel<true, 1>, attention_tc128_kernel<true, 2>,
-         attention_tc128_kernel<true, 3>}};
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      for (int i = 0; i < 8; ++i) {
-        cudaError_t c1 = cudaFuncSetAttribute(k2[i >> 2][i & 3], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (i >> 2) ? Lay2<true>::SMEM : Lay2<false>::SMEM);
-        if (c1 != cudaSuccess) {
-          err = std::string("cudaFuncSetAttribute(attention_tc128_kernel): ") + cudaGetErrorString(c1);
-          return -1;
-        }
-      }
-      attr2_set = true;
-    }
-    // Q, K and V tiles are all [128 rows x 64]: one tensor map
-    launch_pdl(k2[bsel][var], dim3(grid), dim3(192), bsel ? Lay2<true>::SMEM : Lay2<false>::SMEM, st, tmq, tmq, a,
-               (int)items, step);
-  } else {
-    launch_pdl(kern[bsel][var], dim3(grid), dim3(192), bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st, tmq, tmkv, a,
-               (int)items, step);
-  }
+  launch_pdl(kern[bsel][var], dim3(grid), dim3(192), bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st, tmq, tmkv, a,
+             (int)items, step);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("attention_tc launch: ") + cudaGetErrorString(ce);

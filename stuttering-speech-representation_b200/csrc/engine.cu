@@ -1929,10 +1929,6 @@ int ssr_tuning_set(const char* key, int32_t value) {
     g_pdl = value != 0;
     return 0;
   }
-  if (k == "attention_block") {
-    g_attention_block = value == 64 ? 64 : 128;
-    return 0;
-  }
   if (k == "attention_paired") {
     g_attention_paired = value != 0;
     return 0;
