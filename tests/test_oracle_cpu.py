@@ -178,8 +178,29 @@ def test_whisper_decoder_oracle_vs_reference_golden():
     assert g["decoder"].shape == (4, 3, 256)
 
 
+def test_whisper_oracle_vs_reference_golden_at_large_width():
+    """The oracle against the reference's own output at Whisper-large's width (d = 1280, 20 heads, F = 5120; 2 + 2
+    layers): encoder_layer_* and decoder_layer_* of one clip of tests/golden/whisper_wide_full.npz."""
+    from oracle.whisper_oracle import WhisperDecoderTokenOracle, WhisperEncoderOracle, log_mel
+    from ssr_b200 import synth
+    from ssr_b200.melfilters import whisper_mel_filters
+
+    g = golden("whisper_wide_full")
+    model, fe = synth.build_whisper_model("wide_full")
+    assert abs(synth.state_checksum(model) - float(g["checksum"])) <= 1e-9 * float(g["checksum"])
+    assert g["encoder"].shape == (4, 3, 1280) and g["decoder"].shape == (4, 3, 1280)
+    eo = WhisperEncoderOracle.from_hf(model.encoder)
+    do = WhisperDecoderTokenOracle.from_hf(model.decoder)
+    clip = synth.mixed_clips()[2]  # the tonal clip with a silent gap
+    hs = eo.hidden_states(log_mel(clip, whisper_mel_filters(80)))
+    enc = np.stack([h.mean(0) for h in hs])
+    dec = np.stack(do.hidden_states(hs[-1]))
+    assert rel_err(enc[None], g["encoder"][2][None]) < 5e-5
+    assert rel_err(dec[None], g["decoder"][2][None]) < 5e-5
+
+
 def test_golden_fixture_shapes():
     assert golden("wavlm_base_plus")["pooled"].shape == (8, 13, 768)
     assert golden("wavlm_large")["pooled"].shape == (7, 25, 1024)
-    assert golden("whisper_large")["pooled"].shape == (2, 33, 1280)
+    assert golden("whisper_large")["pooled"].shape == (3, 33, 1280)  # third clip: a full 30 s window
     assert golden("whisper_tiny")["pooled"].shape == (6, 3, 256)
