@@ -454,6 +454,11 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
+        if args.gather == "overlap":
+            # The gather has a whole step (~35 ms) to land ~26 MB per peer: two channels are plenty, and every NCCL
+            # CTA that runs next to the forward takes an SM away from a persistent 148-CTA kernel for that long.
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+            os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     peaks = load_peaks()
     for kv in args.tune:
@@ -498,7 +503,8 @@ def main():
         line["sustained"] = {"seconds": round(r["sustained_s"], 2), "steps": r["sustained_steps"],
                              "clocks": r["sustained_clocks"]}
     if world > 1:
-        line["gather"] = {"mode": args.gather, "gather_ok": r["gather_ok"],
+        line["gather"] = {"mode": args.gather, "nccl_max_nchannels": os.environ.get("NCCL_MAX_NCHANNELS"),
+                          "gather_ok": r["gather_ok"],
                           "bytes_landed_per_rank_per_step": int(world * pooled.nbytes)}
         if rank == 0:
             # rank 0 recomputes rank 1's shard (same clips, same batch positions) and compares with what arrived

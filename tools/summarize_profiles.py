@@ -1,7 +1,7 @@
 """Turn the raw outputs of tools/gpu_ncu_bench.sh + a bench.py run (gpurun_out/) into the tracked summaries under
 profiles/: the ncu launch list, kernel-group shares (ncu vs in-run CUDA events), the --set full GEMM capture summary.
 
-    python tools/summarize_profiles.py [round_tag]        # default r01
+    python tools/summarize_profiles.py [round_tag]        # default r02
 """
 import collections
 import csv
@@ -29,7 +29,7 @@ def group_of(name: str) -> str:
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     shutil.copy(os.path.join(OUT, "launches.csv"), os.path.join(PROF, f"{tag}_ncu_launches.csv"))
     shutil.copy(os.path.join(OUT, "bench_final.log"), os.path.join(PROF, f"{tag}_bench_final.log"))
     rows = list(csv.reader(open(os.path.join(OUT, "launches.csv"))))
@@ -76,6 +76,19 @@ def main():
         ix = {k: i for i, k in enumerate(h)}
         summ = [{k: (r[ix[k]][:40] + " " + units[ix[k]]).strip() for k in want if k in ix} for r in rr[2:]]
         json.dump(summ, open(os.path.join(PROF, f"{tag}_gemm_tc2_ncu_full_summary.json"), "w"), indent=1)
+
+        def num(sv):
+            v, u = sv.rsplit(" ", 1) if " " in sv else (sv, "")
+            return float(v.replace(",", "")) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+
+        per = [num(x["dram__bytes_read.sum"]) + num(x["dram__bytes_write.sum"]) for x in summ]
+        traffic = {"kernel": "gemm_tc2_kernel",
+                   "source": "ncu --set full --clock-control none -k regex:gemm_tc2 -s 40 -c 4 on the bench command "
+                             "(one encoder layer's four GEMM launches); tools/gpu_ncu_bench.sh",
+                   "launch_traffic_bytes": [int(v) for v in per],
+                   "traffic_bytes_per_launch_avg": int(sum(per) / max(len(per), 1)),
+                   "algorithmic_bytes_per_launch_avg": 407000000}
+        json.dump(traffic, open(os.path.join(PROF, f"{tag}_gemm_traffic.json"), "w"), indent=1)
         for s in summ:
             print(s["gpu__time_duration.sum"], s["dram__bytes_read.sum"], s["dram__bytes_write.sum"],
                   s["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"])
