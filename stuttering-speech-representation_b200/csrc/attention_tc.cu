@@ -678,423 +678,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 
 
 
-// ====================================================================== three CTAs per SM: P in TMEM, one S buffer
-// The counters of attention_tc_kernel (profiles/r02_attention_analysis.md) say that its softmax warps queue on the
-// MUFU unit while they are in their exponential loops and that the unit idles while both warps of a scheduler are in
-// the fixed-latency part of a block at the same time. This variant puts a THIRD softmax warp on every scheduler:
-//   * P goes to tensor memory (tcgen05.st, bf16 pairs) and P V is issued with the A operand in TMEM: no P buffers in
-//     shared memory, no proxy fence. Shared memory per CTA: Q 16 KB, two 64-key K / V stages 32 KB, 16 KB of output
-//     staging -> three CTAs fit an SM.
-//   * TMEM per CTA: S 64 columns (single buffer) + O 64 + P 32 = 160 columns in two allocations (128 + 32), 480 of the
-//     512 columns of an SM for three CTAs. One S buffer means S of block n+1 is issued when the softmax of block n
-//     arrives; the tensor-core round trip that follows is what the other two CTAs cover.
-//   * 112 registers per thread (192 threads x 3 CTAs): a block's scores live in two 32-register chunks.
-constexpr int S3_Q = 0;
-constexpr int S3_K = Q_BYTES;                    // 2 stages of [64 x 64] bf16
-constexpr int S3_V = S3_K + 2 * KV_BYTES;
-constexpr int S3_STAGE = S3_V + 2 * KV_BYTES;    // epilogue transposition [128 x 64] bf16
-constexpr int S3_BAR = S3_STAGE + Q_BYTES;
-constexpr int S3_LEN = S3_BAR + 192;
-constexpr int S3_WIN = S3_BAR + 256;
-template <bool HAS_BIAS>
-struct Lay3 {
-  static constexpr int SM_GATE = S3_WIN + (HAS_BIAS ? 4 * WIN * 4 : 0);
-  static constexpr int SMEM = SM_GATE + (HAS_BIAS ? 2 * 128 * 4 : 0);
-  static_assert(3 * (SMEM + 1024) <= 228 * 1024, "three CTAs per SM");
-};
-constexpr int T3_S = 0, T3_O = 64;  // inside the 128-column allocation; P is the 32-column allocation
-
-// One 32-key chunk: scores -> (bias, mask) -> running maximum and / or probabilities (bf16 pairs in pk[16]).
-template <bool HAS_BIAS, bool MASK, bool WRITE_P, bool TRACK_MAX, bool POLY, bool PACK2>
-__device__ __forceinline__ void chunk2(const uint32_t (&raw)[32], int jg0, int len, float gate, const float* rel,
-                                       float mu2, float& m_blk, float& l_blk, uint32_t (&pk)[16]) {
-  uint64_t l2 = 0;
-  const uint64_t scale2 = pack2(LOG2E, LOG2E), shift2 = pack2(-mu2, -mu2), gate2 = pack2(gate, gate);
-#pragma unroll
-  for (int k = 0; k < 32; k += 2) {
-    float v0 = __uint_as_float(raw[k]), v1 = __uint_as_float(raw[k + 1]);
-    if (HAS_BIAS) {
-      if (PACK2) {
-        unpack2(fma2(gate2, pack2(rel[k], rel[k + 1]), pack2(v0, v1)), v0, v1);
-      } else {
-        v0 = fmaf(gate, rel[k], v0);
-        v1 = fmaf(gate, rel[k + 1], v1);
-      }
-    }
-    if (MASK) {
-      if (jg0 + k >= len) v0 = -INFINITY;
-      if (jg0 + k + 1 >= len) v1 = -INFINITY;
-    }
-    if (TRACK_MAX) m_blk = fmaxf(m_blk, fmaxf(v0, v1));
-    if (WRITE_P) {
-      const bool poly = POLY && (k & 6) == 0;
-      float x0, x1;
-      if (PACK2) {
-        unpack2(fma2(pack2(v0, v1), scale2, shift2), x0, x1);
-      } else {
-        x0 = fmaf(v0, LOG2E, -mu2);
-        x1 = fmaf(v1, LOG2E, -mu2);
-      }
-      const float p0 = poly ? ex2_poly(x0) : ex2_approx(x0);
-      const float p1 = poly ? ex2_poly(x1) : ex2_approx(x1);
-      if (PACK2)
-        l2 = add2(l2, pack2(p0, p1));
-      else
-        l_blk += p0 + p1;
-      __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);  // low half = even key: the TMEM A-operand packing
-      pk[k >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-    }
-  }
-  if (WRITE_P && PACK2) {
-    float la, lb;
-    unpack2(l2, la, lb);
-    l_blk += la + lb;
-  }
-}
-
-
-// 256 threads: warpgroup 0 = the four softmax warps, warpgroup 1 = TMA producer (warp 4), MMA issuer (warp 5) and two
-// idle warps. setmaxnreg moves registers from warpgroup 1 (24 each) to warpgroup 0 (136 each): 3 CTAs x 256 threads
-// x 80 registers at launch is the whole register file.
-template <bool HAS_BIAS, int VAR>
-__global__ void __launch_bounds__(256, 3)
-attention_tc3_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmkv,
-                     const AttentionArgs a, const int n_items, const Step step) {
-  constexpr bool PACK2 = (VAR & 1) != 0, POLY = (VAR & 2) != 0;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S3_BAR);
-  uint64_t* q_full = bars + 0;
-  uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;    // [2]
-  uint64_t* k_empty = bars + 4;   // [2]
-  uint64_t* v_full = bars + 6;    // [2]
-  uint64_t* v_empty = bars + 8;   // [2]
-  uint64_t* bar_s = bars + 10;
-  uint64_t* bar_p = bars + 11;
-  uint64_t* bar_o = bars + 12;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);  // [2]: the 128- and the 32-column allocation
-
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    if (smem_u32(smem) & 1023) __trap();
-    prefetch_tmap(&tmq);
-    prefetch_tmap(&tmkv);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&bar_o[i], 1);
-    }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    fence_mbar_init();
-  }
-  if (warp == 5) {
-    tmem_alloc(tmem_slot, 128);
-    tmem_alloc(tmem_slot + 1, 32);
-    tmem_relinquish();
-  }
-  if (HAS_BIAS && threadIdx.x < 128) {
-    float* g0 = reinterpret_cast<float*>(smem + Lay3<HAS_BIAS>::SM_GATE);
-    g0[threadIdx.x] = 0.f;
-    g0[128 + threadIdx.x] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_slot[0], tmem_p = tmem_slot[1];
-  griddep_wait();
-  griddep_launch();
-  if (warp >= 4)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-  else
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
-
-  if (threadIdx.x == 128) {
-    // ============================ TMA producer ============================
-    uint32_t n_item = 0, n = 0;
-    Cursor cur;
-    cur.init(a, step);
-    int* lsm = reinterpret_cast<int*>(smem + S3_LEN) + 8;
-    uint32_t lbuf = 0;
-    ItemPre nxt = cur.load(a, lsm);
-    cp_async_commit();
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
-      cp_async_wait_all();
-      const Item it = finish_item(a, nxt, lsm[lbuf]);
-      if (idx + (int)gridDim.x < n_items) {
-        cur.advance(a, step);
-        nxt = cur.load(a, lsm + (lbuf ^ 1));
-        cp_async_commit();
-      }
-      if (!it.valid) continue;
-      const int row0 = it.b * a.slot;
-      mbar_wait(q_empty, (n_item & 1) ^ 1);
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(smem + S3_Q, &tmq, q_full, it.h * HD, row0 + it.q0);
-      for (int j = 0; j < it.nkb; ++j, ++n) {
-        const int s = n & 1;
-        const uint32_t ph = ((n >> 1) & 1) ^ 1;
-        mbar_wait(&k_empty[s], ph);
-        mbar_arrive_expect_tx(&k_full[s], KV_BYTES);
-        tma_load_2d(smem + S3_K + s * KV_BYTES, &tmkv, &k_full[s], a.D + it.h * HD, row0 + j * KBLK);
-        mbar_wait(&v_empty[s], ph);
-        mbar_arrive_expect_tx(&v_full[s], KV_BYTES);
-        tma_load_2d(smem + S3_V + s * KV_BYTES, &tmkv, &v_full[s], 2 * a.D + it.h * HD, row0 + j * KBLK);
-      }
-      ++n_item;
-    }
-  } else if (threadIdx.x == 160) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
-    const uint64_t dq = umma_desc_sw128(smem_u32(smem + S3_Q));
-    uint32_t n_item = 0, n = 0;
-    bool have_prev = false, prev_first = false;
-    int prev_n16 = 0;
-    auto issue_pv_prev = [&]() {
-      const uint32_t pn = n - 1;
-      const int ps = pn & 1;
-      mbar_wait(&v_full[ps], (pn >> 1) & 1);
-      tc_fence_after();
-      const uint64_t dv = umma_desc_sw128_mn(smem_u32(smem + S3_V + ps * KV_BYTES));
-      for (int k = 0; k < prev_n16; ++k)
-        umma_bf16_ts(tmem + T3_O, tmem_p + 8 * k, dv + (uint64_t)(k * 2048 >> 4), idesc_pv,
-                     (!prev_first || k != 0) ? 1u : 0u);
-      umma_commit(&v_empty[ps]);
-      umma_commit(&bar_o[pn & 1]);
-    };
-    Cursor cur;
-    cur.init(a, step);
-    int* lsm = reinterpret_cast<int*>(smem + S3_LEN) + 10;
-    uint32_t lbuf = 0;
-    ItemPre nxt = cur.load(a, lsm);
-    cp_async_commit();
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
-      cp_async_wait_all();
-      const Item it = finish_item(a, nxt, lsm[lbuf]);
-      if (idx + (int)gridDim.x < n_items) {
-        cur.advance(a, step);
-        nxt = cur.load(a, lsm + (lbuf ^ 1));
-        cp_async_commit();
-      }
-      if (!it.valid) continue;
-      mbar_wait(q_full, n_item & 1);
-      for (int j = 0; j < it.nkb; ++j) {
-        const int s = n & 1;
-        const int nlive = min(KBLK, it.len - j * KBLK);
-        const int n16 = (nlive + 15) >> 4;
-        mbar_wait(&k_full[s], (n >> 1) & 1);
-        if (have_prev) mbar_wait(bar_p, (n - 1) & 1);  // the S and the P buffer are free
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_u32(smem + S3_K + s * KV_BYTES));
-        const uint32_t idesc_s = umma_idesc_bf16(128, n16 * 16);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + T3_S, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        if (j == it.nkb - 1) umma_commit(q_empty);
-        umma_commit(&k_empty[s]);
-        umma_commit(bar_s);
-        if (have_prev) issue_pv_prev();
-        have_prev = true;
-        prev_n16 = n16;
-        prev_first = (j == 0);
-        ++n;
-      }
-      mbar_wait(bar_p, (n - 1) & 1);
-      tc_fence_after();
-      issue_pv_prev();
-      have_prev = false;
-      ++n_item;
-    }
-  } else if (warp < 4) {
-    // ============================ softmax / output warps ============================
-    const uint32_t quad = warp;
-    const int il = quad * 32 + lane;
-    const uint32_t lane_addr = (quad * 32u) << 16;
-    uint32_t n = 0;
-    Cursor cur;
-    cur.init(a, step);
-    int* lsm = reinterpret_cast<int*>(smem + S3_LEN) + quad * 2;
-    ItemPre nxt = cur.load(a, lsm, lane == 0);
-    float* gsm = reinterpret_cast<float*>(smem + Lay3<HAS_BIAS>::SM_GATE) + il;
-    uint32_t gbuf = 0;
-    auto prefetch_gate = [&](const ItemPre& p, uint32_t buf) {
-      if (HAS_BIAS && p.q0 + il < a.slot)
-        cp_async_f32(gsm + buf * 128, a.gate + ((long long)p.b * a.slot + p.q0 + il) * a.H + p.h);
-      cp_async_commit();
-    };
-    prefetch_gate(nxt, 0);
-    float* win = reinterpret_cast<float*>(smem + S3_WIN) + quad * WIN;
-    const float* rel = win + 31 - lane;
-    const uint32_t ts = tmem + lane_addr + T3_S, tp = tmem_p + lane_addr, to = tmem + lane_addr + T3_O;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, gbuf ^= 1) {
-      cp_async_wait_all();
-      __syncwarp();
-      const Item it = finish_item(a, nxt, lsm[gbuf]);
-      float gate = 0.f;
-      if (HAS_BIAS) gate = gsm[gbuf * 128];
-      if (idx + (int)gridDim.x < n_items) {
-        cur.advance(a, step);
-        nxt = cur.load(a, lsm + (gbuf ^ 1), lane == 0);
-        prefetch_gate(nxt, gbuf ^ 1);
-      }
-      if (!it.valid) continue;
-      const int row0 = it.b * a.slot;
-      const bool warp_live = it.q0 + (int)quad * 32 < it.len;
-      const float* table = nullptr;
-      int win_base = 0;
-      if (HAS_BIAS) {
-        table = a.relbias + (long long)it.h * a.rel_stride;
-        win_base = a.rel_center - 31 - (it.q0 + (int)quad * 32);
-      }
-      constexpr float L_SAFE = 1.8446744e19f * 64.0f;  // 2^70
-      float m_ref = -INFINITY, l_run = 0.f;
-      for (int j = 0; j < it.nkb; ++j, ++n) {
-        const int k0 = j * KBLK;
-        const int nlive = min(KBLK, it.len - k0);
-        const int nch = (nlive + 31) >> 5;
-        const bool need_mask = (nlive & 31) != 0;
-        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        if (HAS_BIAS && warp_live) {
-          const int t0 = win_base + k0 + (int)lane, hi = a.rel_stride - 1;
-          w0 = __ldg(table + min(max(t0, 0), hi));
-          w1 = __ldg(table + min(max(t0 + 32, 0), hi));
-          w2 = __ldg(table + min(max(t0 + 64, 0), hi));
-        }
-        mbar_wait(bar_s, n & 1);
-        __syncwarp();
-        tc_fence_after();
-        if (warp_live) {
-          if (HAS_BIAS) {
-            win[lane] = w0;
-            win[lane + 32] = w1;
-            win[lane + 64] = w2;
-            __syncwarp();
-          }
-          uint32_t ra[32], rb[32], pk[16];
-          float dummy = 0.f;
-          tmem_ld_32x32(ts, ra);
-          if (nch == 2) tmem_ld_32x32(ts + 32, rb);
-          tmem_wait_ld();
-          if (j == 0) {
-            float m_blk = -INFINITY;
-            if (nch == 2) {
-              chunk2<HAS_BIAS, false, false, true, false, PACK2>(ra, k0, it.len, gate, rel, 0.f, m_blk, dummy, pk);
-              chunk2<HAS_BIAS, true, false, true, false, PACK2>(rb, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, dummy, pk);
-            } else {
-              chunk2<HAS_BIAS, true, false, true, false, PACK2>(ra, k0, it.len, gate, rel, 0.f, m_blk, dummy, pk);
-            }
-            m_ref = m_blk;
-          }
-          auto exp_pass = [&](float mu2, float& l_blk, bool all_masked) {
-            if ((nch == 1 && need_mask) || all_masked)
-              chunk2<HAS_BIAS, true, true, false, POLY, PACK2>(ra, k0, it.len, gate, rel, mu2, dummy, l_blk, pk);
-            else
-              chunk2<HAS_BIAS, false, true, false, POLY, PACK2>(ra, k0, it.len, gate, rel, mu2, dummy, l_blk, pk);
-            if (j > 0) {
-              // one P buffer: P_{n-1} V_{n-1} (issued after S_n) must have retired before P is overwritten
-              mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
-              tc_fence_after();
-            }
-            tmem_st_32x16(tp, pk);
-            if (nch == 2) {
-              if (need_mask || all_masked)
-                chunk2<HAS_BIAS, true, true, false, POLY, PACK2>(rb, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, pk);
-              else
-                chunk2<HAS_BIAS, false, true, false, POLY, PACK2>(rb, k0 + 32, it.len, gate, rel + 32, mu2, dummy, l_blk, pk);
-              tmem_st_32x16(tp + 16, pk);
-            }
-          };
-          float mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-          float l_blk = 0.f;
-          exp_pass(mu2, l_blk, false);
-          const bool unsafe = !(l_blk < L_SAFE);
-          if (j > 0 && __any_sync(0xffffffffu, unsafe)) {
-            float m_blk = -INFINITY;
-            chunk2<HAS_BIAS, true, false, true, false, PACK2>(ra, k0, it.len, gate, rel, 0.f, m_blk, dummy, pk);
-            if (nch == 2)
-              chunk2<HAS_BIAS, true, false, true, false, PACK2>(rb, k0 + 32, it.len, gate, rel + 32, 0.f, m_blk, dummy, pk);
-            const float m_new = unsafe ? fmaxf(m_ref, m_blk) : m_ref;
-            const float alpha = (m_new == m_ref) ? 1.f : ex2_approx((m_ref - m_new) * LOG2E);
-            m_ref = m_new;
-            mu2 = ((m_ref == -INFINITY) ? 0.f : m_ref) * LOG2E;
-            l_run *= alpha;
-            tmem_wait_st();
-            {
-              uint32_t o0[32];
-              for (int hh = 0; hh < 2; ++hh) {  // O is stable: P_{n-1} V_{n-1} has retired (bar_o above)
-                tmem_ld_32x32(to + hh * 32, o0);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) o0[k] = __float_as_uint(__uint_as_float(o0[k]) * alpha);
-                tmem_st_32x32(to + hh * 32, o0);
-                tmem_wait_st();
-              }
-            }
-            l_blk = 0.f;
-            exp_pass(mu2, l_blk, true);
-          }
-          l_run += l_blk;
-          tmem_wait_st();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_p);
-      }
-      mbar_wait(&bar_o[(n - 1) & 1], ((n - 1) >> 1) & 1);
-      __syncwarp();
-      tc_fence_after();
-      if (warp_live) {
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-        uint8_t* stage = smem + S3_STAGE + quad * 32 * 128;
-        uint8_t* mine = stage + lane * 128;
-        const uint32_t sw = lane & 7;
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t o0[32];
-          tmem_ld_32x32(to + hh * 32, o0);
-          tmem_wait_ld();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t wv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = q * 8 + 2 * e;
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(o0[c]) * inv, __uint_as_float(o0[c + 1]) * inv);
-              wv[e] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            *reinterpret_cast<uint4*>(mine + (((hh * 4 + q) ^ sw) * 16)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-          }
-        }
-        __syncwarp();
-        {
-          const uint32_t rsub = lane >> 3, cch = lane & 7;
-          bf16* dst = a.out + ((long long)row0 + it.q0 + quad * 32) * a.D + it.h * HD + cch * 8;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const uint32_t r = t * 4 + rsub;
-            const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((cch ^ (r & 7)) * 16));
-            if (it.q0 + (int)(quad * 32 + r) < it.len) *reinterpret_cast<uint4*>(dst + (long long)r * a.D) = v;
-          }
-        }
-        __syncwarp();
-      }
-      tc_fence_before();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem, 128);
-    tmem_dealloc(tmem_p, 32);
-  }
-}
-
 }  // namespace
 
 // Kernel variant (see attention_tc_kernel: bit 0 = packed pair arithmetic, bit 1 = polynomial exp2 share);
@@ -1102,8 +685,6 @@ attention_tc3_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_const
 int g_attention_variant = 1;
 // 1: two-tile clips use the paired item order (see Cursor); 0: query-tile-major order everywhere.
 int g_attention_paired = 1;
-// CTAs per SM: 3 = attention_tc3_kernel (P in tensor memory, one S buffer), 2 = attention_tc_kernel.
-int g_attention_ctas = 3;
 
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err) {
   if (a.D != a.H * HD) {
@@ -1156,42 +737,8 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   }
   const int bsel = a.gate != nullptr ? 1 : 0;
   const int var = g_attention_variant & 3;
-  if (g_attention_ctas == 3) {
-    static const KernelFn k3[2][4] = {
-        {attention_tc3_kernel<false, 0>, attention_tc3_kernel<false, 1>, attention_tc3_kernel<false, 2>,
-         attention_tc3_kernel<false, 3>},
-        {attention_tc3_kernel<true, 0>, attention_tc3_kernel<true, 1>, attention_tc3_kernel<true, 2>,
-         attention_tc3_kernel<true, 3>}};
-    static bool attr3_set = false;
-    if (!attr3_set) {
-      for (int i = 0; i < 8; ++i) {
-        cudaError_t c1 = cudaFuncSetAttribute(k3[i >> 2][i & 3], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (i >> 2) ? Lay3<true>::SMEM : Lay3<false>::SMEM);
-        if (c1 != cudaSuccess) {
-          err = std::string("cudaFuncSetAttribute(attention_tc3_kernel): ") + cudaGetErrorString(c1);
-          return -1;
-        }
-      }
-      attr3_set = true;
-    }
-    const int grid3 = (int)(items < 3LL * num_sms ? items : 3LL * num_sms);
-    Step step3 = step;
-    step3.dq = grid3 / (a.B * a.H);
-    step3.db = (grid3 % (a.B * a.H)) / a.H;
-    step3.dh = grid3 % a.H;
-    step3.paired = 0;
-    if (g_attention_paired && ceil_div(a.slot, QT) == 2 && (grid3 & 1) == 0) {
-      step3.paired = 1;
-      step3.dq = 0;
-      step3.db = (grid3 / 2) / a.H;
-      step3.dh = (grid3 / 2) % a.H;
-    }
-    launch_pdl(k3[bsel][var], dim3(grid3), dim3(256), bsel ? Lay3<true>::SMEM : Lay3<false>::SMEM, st, tmq, tmkv, a,
-               (int)items, step3);
-  } else {
-    launch_pdl(kern[bsel][var], dim3(grid), dim3(192), bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st, tmq, tmkv, a,
-               (int)items, step);
-  }
+  launch_pdl(kern[bsel][var], dim3(grid), dim3(192), bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st, tmq, tmkv, a,
+             (int)items, step);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     err = std::string("attention_tc launch: ") + cudaGetErrorString(ce);

@@ -1929,10 +1929,6 @@ int ssr_tuning_set(const char* key, int32_t value) {
     g_pdl = value != 0;
     return 0;
   }
-  if (k == "attention_ctas") {
-    g_attention_ctas = value == 2 ? 2 : 3;
-    return 0;
-  }
   if (k == "attention_paired") {
     g_attention_paired = value != 0;
     return 0;

@@ -54,7 +54,6 @@ int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
 extern int g_attention_variant;  // attention_tc.cu kernel variant (process-wide tuning knob)
 extern int g_attention_paired;   // 1: paired item order for two-tile clips
-extern int g_attention_ctas;     // 3: three CTAs per SM (P in TMEM), 2: two (P in shared memory)
 
 // Whisper decoder single-token cross-attention (decoder.cu). All token-level tensors have one row per clip.
 struct DecCrossArgs {

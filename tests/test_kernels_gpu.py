@@ -9,7 +9,6 @@ pytestmark = pytest.mark.gpu
 
 
 DEFAULT_VARIANT = 1  # csrc/attention_tc.cu g_attention_variant
-DEFAULT_CTAS = 3     # csrc/attention_tc.cu g_attention_ctas
 
 
 def _lib():
@@ -207,22 +206,20 @@ def test_attention(slot, H, lens, bias, impl):
             assert (got[b, :L] - ref[b, :L]).abs().max().item() < 2e-2, f"query-tile-major order, clip {b}"
     # every variant of the tcgen05 kernel (S prefetch from TMEM, polynomial exp2 share) must hold the same tolerance
     # every arithmetic variant of the tcgen05 kernel (packed pairs, polynomial exp2 share) must hold the same tolerance
-    for ctas, variant in ([(c, v) for c in (3, 2) for v in (0, 1, 2, 3)] if impl == 0 else [(2, DEFAULT_VARIANT)]):
+    for variant in ([0, 1, 2, 3] if impl == 0 else [DEFAULT_VARIANT]):
         assert lib.ssr_tuning_set(b"attention_variant", variant) == 0
-        assert lib.ssr_tuning_set(b"attention_ctas", ctas) == 0
         out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
         e = _err()
         rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), _ptr(gate), _ptr(relb),
                                2 * R - 1, R - 1, impl, None, e, 512)
         torch.cuda.synchronize()
         lib.ssr_tuning_set(b"attention_variant", DEFAULT_VARIANT)
-        lib.ssr_tuning_set(b"attention_ctas", DEFAULT_CTAS)
         assert rc == 0, e.value.decode()
         got = out.float().view(B, slot, D)
         for b in range(B):
             L = int(lens_t[b])
             err = (got[b, :L] - ref[b, :L]).abs().max().item()
-            assert err < 2e-2, f"ctas {ctas}, variant {variant}, clip {b}: max err {err}"
+            assert err < 2e-2, f"variant {variant}, clip {b}: max err {err}"
 
 
 @pytest.mark.parametrize("scale", [1.0, 6.0, 40.0])
@@ -246,23 +243,21 @@ def test_attention_stale_reference_and_rescale(scale):
     qkv = qkv.bfloat16()
     lens_t = torch.tensor([slot, 517], device="cuda", dtype=torch.int32)
     ref = _attn_ref(qkv, B, slot, H, lens_t, None, None, 0).view(B, slot, D)
-    for ctas, variant in [(c, v) for c in (3, 2) for v in range(4)]:  # the rescale path of both kernels
+    for variant in range(4):  # the rescale path under every arithmetic variant
         assert lib.ssr_tuning_set(b"attention_variant", variant) == 0
-        assert lib.ssr_tuning_set(b"attention_ctas", ctas) == 0
         out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
         e = _err()
         rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), None, None, 0, 0, 0,
                                None, e, 512)
         torch.cuda.synchronize()
         lib.ssr_tuning_set(b"attention_variant", DEFAULT_VARIANT)
-        lib.ssr_tuning_set(b"attention_ctas", DEFAULT_CTAS)
         assert rc == 0, e.value.decode()
         got = out.float().view(B, slot, D)
         assert torch.isfinite(got).all()
         for b in range(B):
             L = int(lens_t[b])
             err = (got[b, :L] - ref[b, :L]).abs().max().item()
-            assert err < 2e-2, f"ctas {ctas}, variant {variant}, clip {b}: max err {err}"
+            assert err < 2e-2, f"variant {variant}, clip {b}: max err {err}"
 
 
 def test_pool_mean():

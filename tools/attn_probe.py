@@ -42,10 +42,11 @@ def run(name, B, slot, H, length, bias, reps=5):
     print(f"{name:8s} max |tc - simt| over live rows = {diff:.3e}", flush=True)
     # (outputs are bf16: one ulp at |o| in [4, 8) is 3.1e-2; the GPU tests assert, this probe only reports)
     fl = 4.0 * B * H * length * length * 64
-    combos = [(c, 1, v) for c in (3, 2) for v in (1, 0)]
+    combos = [(1, v) for v in (0, 1, 2, 3)]
+    if 128 < slot <= 256:
+        combos += [(0, v) for v in (0, 1)]
     combos += combos[:2]
-    for ctas, paired, variant in combos:
-        lib.ssr_tuning_set(b"attention_ctas", ctas)
+    for paired, variant in combos:
         lib.ssr_tuning_set(b"attention_paired", paired)
         lib.ssr_tuning_set(b"attention_variant", variant)
         call()
@@ -58,11 +59,10 @@ def run(name, B, slot, H, length, bias, reps=5):
         ev[1].record()
         torch.cuda.synchronize()
         ms = ev[0].elapsed_time(ev[1]) / reps
-        print(f"{name:8s} ctas {ctas} paired {paired} variant {variant} B={B} slot={slot} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s "
+        print(f"{name:8s} paired {paired} variant {variant} B={B} slot={slot} H={H}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s "
               f"(live)  max|tc - simt| {d:.3e}", flush=True)
     lib.ssr_tuning_set(b"attention_variant", DEFAULT_VARIANT)
     lib.ssr_tuning_set(b"attention_paired", 1)
-    lib.ssr_tuning_set(b"attention_ctas", 3)
 
 
 if __name__ == "__main__":
