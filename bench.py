@@ -382,9 +382,12 @@ def hf_gpu_baseline(model, prep, x_np, steps: int, local: int) -> dict:
     the CPU-side feature extraction is outside the timed region (favours this baseline)."""
     import torch
 
+    import copy
+
     dev = torch.device(f"cuda:{local}")
     out = {}
     x0 = prep(torch.from_numpy(x_np).to(dev))
+    model = copy.deepcopy(model)  # the caller's fp32 weights must survive the bf16 round trip below
     for name, dtype in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
         try:
             m = model.to(dev).to(dtype).eval()
@@ -408,7 +411,7 @@ def hf_gpu_baseline(model, prep, x_np, steps: int, local: int) -> dict:
         except Exception as e:  # noqa: BLE001 - e.g. out of memory: reported, not fatal
             out[name] = {"error": str(e)[:160]}
         torch.cuda.empty_cache()
-    model.to("cpu").to(torch.float32)
+    del model
     torch.cuda.empty_cache()
     return out
 

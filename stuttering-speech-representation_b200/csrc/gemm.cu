@@ -524,8 +524,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // Only the group's weights stream (8 KB per tap) through a TMA ring. Compared with re-loading a shifted A tile per
 // tap this removes ~2/3 of the L2 traffic.
 constexpr int PC_XWIN_BYTES = 3 * 128 * 128;  // 384 rows x 64 bf16
-constexpr int PC_W_BYTES = 64 * 64 * 2;
-constexpr int PC_WSTAGES = 12;  // 96 KB of weight tiles in flight (TMA latency x 8 KB / ~300 cycles per tap)
+constexpr int PC_TAP_BYTES = 64 * 64 * 2;  // one tap's [64 out x 64 in] weight tile
+constexpr int PC_TAPS = 4;                 // taps per ring stage: the MMA thread pays one barrier wait per 32 MMAs
+constexpr int PC_W_BYTES = PC_TAPS * PC_TAP_BYTES;
+constexpr int PC_WSTAGES = 3;  // 96 KB of weight tiles in flight
 constexpr int PC_BAR_OFF = 2 * PC_XWIN_BYTES + PC_WSTAGES * PC_W_BYTES;
 constexpr int PC_STAGE_OFF = PC_BAR_OFF + 512;  // (8 + 2 * PC_WSTAGES) mbarriers + the TMEM base slot
 constexpr int PC_SMEM_BYTES = PC_STAGE_OFF + 4 * (int)sizeof(EpiStage);
@@ -597,11 +599,13 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
       for (int i = 0; i < 3; ++i)
         tma_load_2d(sX + xb * PC_XWIN_BYTES + i * 128 * 128, &tmX, &x_full[xb], g * 64, rowbase + i * 128);
-      for (int tap = 0; tap < 128; ++tap, ++nw) {
+      for (int tap0 = 0; tap0 < 128; tap0 += PC_TAPS, ++nw) {
         const int s = nw % PC_WSTAGES;
         mbar_wait(&w_empty[s], ((nw / PC_WSTAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&w_full[s], PC_W_BYTES);
-        tma_load_2d(sW + s * PC_W_BYTES, &tmW, &w_full[s], tap * 64, g * 64);
+#pragma unroll
+        for (int t = 0; t < PC_TAPS; ++t)
+          tma_load_2d(sW + s * PC_W_BYTES + t * PC_TAP_BYTES, &tmW, &w_full[s], (tap0 + t) * 64, g * 64);
       }
     }
   } else if (threadIdx.x == 160) {
@@ -614,19 +618,23 @@ posconv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait(&x_full[xb], (n >> 1) & 1);
       tc_fence_after();
       const uint64_t dx = umma_desc_sw128(smem_u32(sX + xb * PC_XWIN_BYTES));
-      for (int tap = 0; tap < 128; ++tap, ++nw) {
+      for (int tap0 = 0; tap0 < 128; tap0 += PC_TAPS, ++nw) {
         const int s = nw % PC_WSTAGES;
         mbar_wait(&w_full[s], (nw / PC_WSTAGES) & 1);
         tc_fence_after();
-        const uint64_t dw = umma_desc_sw128(smem_u32(sW + s * PC_W_BYTES));
-        // window shifted by `tap` rows: +tap*128 B in the descriptor's start-address field (16-byte units)
-        const uint64_t da = dx + (uint64_t)(tap * 8);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int t = 0; t < PC_TAPS; ++t) {
+          const int tap = tap0 + t;
+          const uint64_t dw = umma_desc_sw128(smem_u32(sW + s * PC_W_BYTES + t * PC_TAP_BYTES));
+          // window shifted by `tap` rows: +tap*128 B in the descriptor's start-address field (16-byte units)
+          const uint64_t da = dx + (uint64_t)(tap * 8);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + acc * 128 + half * 64, da + (uint64_t)(half * 1024 + 2 * k), dw + 2 * k, idesc,
-                      (tap | k) != 0 ? 1u : 0u);
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + acc * 128 + half * 64, da + (uint64_t)(half * 1024 + 2 * k), dw + 2 * k, idesc,
+                        (tap | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&w_empty[s]);
       }
