@@ -162,21 +162,34 @@ def workload_config(batch: int, n_gpus: int) -> dict:
 
 # ---------------------------------------------------------------------------------------------- our arm
 class StepRunner:
-    """One bench step = one forward of the local shard (+ for N > 1 the all-gather of the pooled embeddings: `inline`
-    on the compute stream, `overlap` on a side stream into double-buffered outputs so that it overlaps the next
-    step's forward)."""
+    """One bench step = one forward of the local shard (+ for N > 1 the all-gather of the pooled embeddings).
+    Gather modes: `inline` — NCCL on the compute stream; `overlap` — NCCL on a side stream into double-buffered outputs,
+    overlapping the next step's forward; `ce` — the same overlap, but the gather is N peer copies out of symmetric
+    memory on the COPY ENGINES (torch.distributed._symmetric_memory: the forward writes its pooled output into a
+    symmetric buffer, two device-side barriers bracket the copies), so that no SM is taken from the forward's
+    persistent kernels."""
 
     def __init__(self, eng, audio, n_samples, world, dev, gather_mode):
         import torch
 
         self.torch, self.eng, self.audio, self.n, self.world, self.dev = torch, eng, audio, n_samples, world, dev
         B, L1, D = audio.shape[0], eng.layers + 1, eng.hidden
+        self.shape = (B, L1, D)
         self.mode = gather_mode if world > 1 else "none"
-        nb = 2 if self.mode == "overlap" else 1
-        self.outs = [torch.empty((B, L1, D), dtype=torch.float32, device=dev) for _ in range(nb)]
+        nb = 2 if self.mode in ("overlap", "ce") else 1
+        self.hdl = None
+        if self.mode == "ce":
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.outs = [symm_mem.empty(B, L1, D, dtype=torch.float32, device=dev) for _ in range(nb)]
+            self.hdl = [symm_mem.rendezvous(t, dist.group.WORLD) for t in self.outs]
+            self.rank = dist.get_rank()
+        else:
+            self.outs = [torch.empty((B, L1, D), dtype=torch.float32, device=dev) for _ in range(nb)]
         self.gath = [torch.empty((world * B, L1, D), dtype=torch.float32, device=dev) for _ in range(nb)] \
             if world > 1 else []
-        self.side = torch.cuda.Stream(dev) if self.mode == "overlap" else None
+        self.side = torch.cuda.Stream(dev) if nb == 2 else None
         self.run_done = [torch.cuda.Event() for _ in range(nb)]
         self.gather_done = [torch.cuda.Event() for _ in range(nb)]
         self.k = 0
@@ -188,7 +201,7 @@ class StepRunner:
         s = self.k % len(self.outs)
         self.k += 1
         cur = torch.cuda.current_stream(self.dev)
-        if self.mode == "overlap":
+        if self.side is not None:
             cur.wait_event(self.gather_done[s])  # the gather issued two steps ago has read outs[s]
         self.eng.pooled_device(self.audio, self.n, out=self.outs[s])
         if self.mode == "inline":
@@ -198,6 +211,18 @@ class StepRunner:
             with torch.cuda.stream(self.side):
                 self.side.wait_event(self.run_done[s])
                 dist.all_gather_into_tensor(self.gath[s], self.outs[s])
+                self.gather_done[s].record(self.side)
+        elif self.mode == "ce":
+            B = self.shape[0]
+            self.run_done[s].record(cur)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.run_done[s])
+                h = self.hdl[s]
+                h.barrier()  # every rank has finished writing its outs[s]
+                for st in range(self.world):
+                    r = (self.rank - st) % self.world
+                    self.gath[s][r * B:(r + 1) * B].copy_(h.get_buffer(r, self.shape, torch.float32), non_blocking=True)
+                h.barrier()  # every rank has finished reading: outs[s] may be overwritten two steps from now
                 self.gather_done[s].record(self.side)
         return s
 
@@ -428,10 +453,11 @@ def main():
     ap.add_argument("--whisper-batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-HF-on-this-GPU baseline")
-    ap.add_argument("--gather", default="inline", choices=["overlap", "inline"],
+    ap.add_argument("--gather", default="inline", choices=["overlap", "inline", "ce"],
                     help="N > 1: all-gather on the compute stream (default), or on a side stream overlapping the next "
                          "step (measured: +1.3 %% at N=2, -1.7 %% at N=4, -1.1 %% at N=8: the NCCL CTAs that run next to "
-                         "the forward take SMs away from its persistent 148-CTA kernels)")
+                         "the forward take SMs away from its persistent 148-CTA kernels), or `ce`: overlapped peer "
+                         "copies out of symmetric memory on the copy engines")
     ap.add_argument("--sustain", type=float, default=5.0, help="seconds of the back-to-back sustained loop (0 = skip)")
     ap.add_argument("--ref-clips", type=int, default=8, help="--impl reference: clips per step")
     ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE",
