@@ -184,8 +184,7 @@ struct ssr_engine {
   cudaStream_t last_stream = nullptr;
   bool last_valid = false;
   // Host-entry pipeline for large batches (the synchronous *_host call is the end-to-end headline): the batch's
-  // audio travels host -> device in chunks on a copy stream while conv0 / conv1 of the chunks that have landed already
-  // run, and the pooled rows of hidden_states[0 .. L-1] travel device -> host while the last layer still computes.
+  // audio travels host -> device in chunks on a copy stream while conv0 of the chunks that have landed already runs, and the pooled rows of hidden_states[0 .. L-1] travel device -> host while the last layer still computes.
   struct HostPipe {
     bool active = false;        // set by run_host around one forward
     int n_chunks = 0, chunk_clips = 0;
@@ -196,6 +195,7 @@ struct ssr_engine {
   } pipe;
   cudaStream_t copy_stream = nullptr;
   int opt_host_pipeline = 1;
+  int opt_host_chunks = 4;  // H2D chunks of the host-entry pipeline (1..8; measured: 4 beats 8 and 2)
   // Small host-entry batches are launch-latency bound (about 210 kernels per WavLM-Large forward): the second
   // identical call (same model path, batch, pitch and lengths — the reference's per-clip loop over equal-length
   // clips) is captured into a CUDA graph and replayed from then on.
@@ -1094,8 +1094,8 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
   if (e->pool_part.ensure((size_t)ceil_div(M, 32) * 2 * D * 4, st, err)) return -1;
 
   // 1. waveform normalisation + conv0 (+ norm + GELU), 2. conv layers 1..6 as implicit GEMMs over the channels-last
-  // signal. With the host pipeline active (run_host, LayerNorm variant) conv0 and conv1 — the two big ones — run
-  // chunk by chunk as the chunks' host-to-device copies land; the small tail layers run once over the whole batch.
+  // signal. With the host pipeline active (run_host, LayerNorm variant) conv0 runs chunk by chunk as the chunks'
+  // host-to-device copies land; the conv GEMMs run once over the whole batch.
   const bool ln = d.feat_norm == SSR_FEAT_NORM_LAYER;
   const bool fused_ln = ln && e->opt_conv_ln_fused && !e->opt_simt;
   const bool piped = e->pipe.active && fused_ln && e->pipe.n_chunks > 1;
@@ -1165,9 +1165,9 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
       if (c0 >= c1) break;
       CK(cudaStreamWaitEvent(st, e->pipe.h2d_done[c], 0));
       if (conv0_range(c0, c1)) return -1;
-      if (conv_range(1, c0, c1)) return -1;
     }
-    first_full_layer = 2;
+    // (conv1 per chunk as well was measured: its 4-CTA-cluster tiles quantise worse on a quarter batch than the
+    // copy time it would hide; conv0 alone, 0.35 ms per chunk, already covers the next chunk's 0.22 ms copy)
   } else {
     if (e->pipe.active)  // pipeline requested but not applicable to this model variant: wait for every chunk
       for (int c = 0; c < e->pipe.n_chunks; ++c) CK(cudaStreamWaitEvent(st, e->pipe.h2d_done[c], 0));
@@ -1609,6 +1609,8 @@ int ssr_set_option(ssr_engine* e, const char* key, int32_t value) {
     e->opt_logmel_dense = value;
   else if (k == "host_pipeline")
     e->opt_host_pipeline = value;
+  else if (k == "host_chunks")
+    e->opt_host_chunks = value;
   else {
     e->err = "unknown option '" + k + "'";
     return -1;
@@ -1782,7 +1784,7 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
     // workspace growth)
     CK(cudaEventRecord(hp.fence, st));
     CK(cudaStreamWaitEvent(cs, hp.fence, 0));
-    hp.n_chunks = wavlm ? 8 : 1;
+    hp.n_chunks = wavlm ? std::max(1, std::min(8, e->opt_host_chunks)) : 1;
     hp.chunk_clips = (B + hp.n_chunks - 1) / hp.n_chunks;
     for (int c = 0; c < hp.n_chunks; ++c) {
       const int c0 = c * hp.chunk_clips, c1 = std::min((int)B, c0 + hp.chunk_clips);
