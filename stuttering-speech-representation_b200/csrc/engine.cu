@@ -187,7 +187,8 @@ struct ssr_engine {
   // audio travels host -> device in chunks on a copy stream while conv0 of the chunks that have landed already runs, and the pooled rows of hidden_states[0 .. L-1] travel device -> host while the last layer still computes.
   struct HostPipe {
     bool active = false;        // set by run_host around one forward
-    int n_chunks = 0, chunk_clips = 0;
+    int n_chunks = 0;
+    int chunk_start[9] = {};  // clip ranges [chunk_start[c], chunk_start[c + 1])
     cudaEvent_t h2d_done[8] = {};
     cudaEvent_t pool_early = nullptr;  // recorded on the compute stream once rows 0 .. L-1 of `pooled` are final
     bool pool_early_recorded = false;
@@ -195,7 +196,7 @@ struct ssr_engine {
   } pipe;
   cudaStream_t copy_stream = nullptr;
   int opt_host_pipeline = 1;
-  int opt_host_chunks = 4;  // H2D chunks of the host-entry pipeline (1..8; measured: 4 beats 8 and 2)
+  int opt_host_chunks = 4;  // H2D chunks of the host-entry pipeline (1..8), geometrically growing sizes (measured best)
   // Small host-entry batches are launch-latency bound (about 210 kernels per WavLM-Large forward): the second
   // identical call (same model path, batch, pitch and lengths — the reference's per-clip loop over equal-length
   // clips) is captured into a CUDA graph and replayed from then on.
@@ -1161,8 +1162,8 @@ int wavlm_forward(ssr_engine* e, const float* audio, int64_t audio_ld, const int
   int first_full_layer = 1;
   if (piped) {
     for (int c = 0; c < e->pipe.n_chunks; ++c) {
-      const int c0 = c * e->pipe.chunk_clips, c1 = std::min(B, c0 + e->pipe.chunk_clips);
-      if (c0 >= c1) break;
+      const int c0 = e->pipe.chunk_start[c], c1 = e->pipe.chunk_start[c + 1];
+      if (c0 >= c1) continue;
       CK(cudaStreamWaitEvent(st, e->pipe.h2d_done[c], 0));
       if (conv0_range(c0, c1)) return -1;
     }
@@ -1784,10 +1785,25 @@ static int run_host(ssr_engine* e, bool wavlm, const float* audio_host, int64_t 
     // workspace growth)
     CK(cudaEventRecord(hp.fence, st));
     CK(cudaStreamWaitEvent(cs, hp.fence, 0));
+    // Chunk sizes grow geometrically: only the FIRST chunk's copy is exposed (nothing to overlap it with), and conv0
+    // of chunk c (~5 us per clip) has to cover the copy of chunk c + 1 (~4 us per clip), so each chunk may be ~1.4x
+    // the one before it. opt_host_chunks caps the count; with 1 the whole batch is one copy.
     hp.n_chunks = wavlm ? std::max(1, std::min(8, e->opt_host_chunks)) : 1;
-    hp.chunk_clips = (B + hp.n_chunks - 1) / hp.n_chunks;
+    {
+      double w[8], tot = 0.0;
+      for (int c = 0; c < hp.n_chunks; ++c) tot += (w[c] = pow(1.4, c));
+      int at = 0;
+      hp.chunk_start[0] = 0;
+      for (int c = 0; c < hp.n_chunks; ++c) {
+        int sz = (int)(B * w[c] / tot + 0.5);
+        if (c == hp.n_chunks - 1 || at + sz > B) sz = B - at;
+        at += sz;
+        hp.chunk_start[c + 1] = at;
+      }
+      hp.chunk_start[hp.n_chunks] = B;
+    }
     for (int c = 0; c < hp.n_chunks; ++c) {
-      const int c0 = c * hp.chunk_clips, c1 = std::min((int)B, c0 + hp.chunk_clips);
+      const int c0 = hp.chunk_start[c], c1 = hp.chunk_start[c + 1];
       if (c0 < c1)
         CK(cudaMemcpyAsync(e->audio_stage.as<float>() + (size_t)c0 * audio_ld, audio_host + (size_t)c0 * audio_ld,
                            (size_t)(c1 - c0) * audio_ld * 4, cudaMemcpyHostToDevice, cs));
