@@ -75,7 +75,8 @@ const char* ssr_last_error(const ssr_engine* e);
  * repeats the previous call's batch size, pitch and lengths — the reference's per-clip loop over equal-length clips),
  * "host_pipeline" (default 1: the *_host entry points move a batch of >= 64 clips host -> device in chunks on a copy
  * stream while the front end already runs on the chunks that have landed, and copy the pooled rows of
- * hidden_states[0 .. L-1] back while the last layer still computes), "logmel_dense" (1 = the dense-DFT log-mel kernel,
+ * hidden_states[0 .. L-1] back while the last layer still computes), "host_chunks" (number of those chunks, 1..8,
+ * default 4, sizes growing geometrically), "logmel_dense" (1 = the dense-DFT log-mel kernel,
  * a cross-check of the default folded-DFT one), "conv_ln_fused" (default 1),
  * "profile" (1 = bracket every kernel launch with CUDA events on the launching stream; read with ssr_profile_fetch).
  * Returns 0, or -1 for an unknown key. */
