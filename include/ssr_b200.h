@@ -125,7 +125,8 @@ int32_t ssr_wavlm_rel_bucket(int32_t rel);
  * "attention_paired" (1, default: clips of two query tiles are walked so that both tiles of a (clip, head) run at the
  * same time on neighbouring CTAs and K / V are read from HBM once; 0: query-tile-major order), "pdl" (1: the per-layer kernels
  * are launched with programmatic stream serialization so that a kernel's prologue overlaps its predecessor's tail;
- * 0, default: plain stream order — measured faster). Returns 0, or -1 for an unknown key. */
+ * 0, default: plain stream order — measured faster), "ln_reverse" / "attention_reverse" (1, default: LayerNorm rows /
+ * attention clips are visited from the end, where the producing kernel's most recent output still sits in L2). Returns 0, or -1 for an unknown key. */
 int ssr_tuning_set(const char* key, int32_t value);
 /* Count of this library's kernel launches since creation (bench.py's gpu_launches). */
 int64_t ssr_launch_count(const ssr_engine* e);

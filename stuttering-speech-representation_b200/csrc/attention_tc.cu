@@ -129,6 +129,7 @@ struct ItemPre {
 struct Step {
   int dq, db, dh;  // gridDim.x in the mixed radix of the item index (host-computed: lives in the constant bank)
   int paired;      // two query tiles per clip (129..256 frames): see Cursor
+  int reverse;     // clips are visited from the last one: the qkv rows the producing GEMM wrote last are still in L2
 };
 // Walks the item list of one CTA (slot s = blockIdx.x + k * gridDim.x, k = 0, 1, ...) without a division per item.
 //   default : s = (qt * B + b) * H + h  (query-tile-major: every CTA sees the same mix of full and partial tiles)
@@ -170,13 +171,13 @@ struct Cursor {
   }
   // The clip length of the item goes global -> shared memory asynchronously (consumed one item later): a value
   // prefetched into a register would be spilled by the compiler at once, i.e. waited for.
-  __device__ __forceinline__ ItemPre load(const AttentionArgs& a, int* len_slot, bool copy = true) const {
+  __device__ __forceinline__ ItemPre load(const AttentionArgs& a, const Step& st, int* len_slot, bool copy = true) const {
     ItemPre p;
-    p.b = b;
+    p.b = st.reverse ? a.B - 1 - b : b;
     p.h = h;
     p.q0 = qt * QT;
     if (copy)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(len_slot)), "l"(a.lens + b) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(len_slot)), "l"(a.lens + p.b) : "memory");
     return p;
   }
 };
@@ -353,14 +354,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     cur.init(a, step);
     int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + 8;  // [2] private to this thread
     uint32_t lbuf = 0;
-    ItemPre nxt = cur.load(a, lsm);
+    ItemPre nxt = cur.load(a, step, lsm);
     cp_async_commit();
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
       cp_async_wait_all();
       const Item it = finish_item(a, nxt, lsm[lbuf]);
       if (idx + (int)gridDim.x < n_items) {  // prefetch the next item's length
         cur.advance(a, step);
-        nxt = cur.load(a, lsm + (lbuf ^ 1));
+        nxt = cur.load(a, step, lsm + (lbuf ^ 1));
         cp_async_commit();
       }
       if (!it.valid) continue;
@@ -409,14 +410,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     cur.init(a, step);
     int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + 10;  // [2] private to this thread
     uint32_t lbuf = 0;
-    ItemPre nxt = cur.load(a, lsm);
+    ItemPre nxt = cur.load(a, step, lsm);
     cp_async_commit();
     for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, lbuf ^= 1) {
       cp_async_wait_all();
       const Item it = finish_item(a, nxt, lsm[lbuf]);
       if (idx + (int)gridDim.x < n_items) {  // prefetch the next item's length
         cur.advance(a, step);
-        nxt = cur.load(a, lsm + (lbuf ^ 1));
+        nxt = cur.load(a, step, lsm + (lbuf ^ 1));
         cp_async_commit();
       }
       if (!it.valid) continue;
@@ -458,7 +459,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
     Cursor cur;
     cur.init(a, step);
     int* lsm = reinterpret_cast<int*>(smem + Lay<HAS_BIAS>::SM_LEN) + quad * 2;  // [2] per warp, copied by lane 0
-    ItemPre nxt = cur.load(a, lsm, lane == 0);
+    ItemPre nxt = cur.load(a, step, lsm, lane == 0);
     // The row's gate of the NEXT item travels global -> shared memory by cp.async (no register is live across the
     // item, so nothing makes the warp wait for the load) and is read one item later; each thread reads its own word.
     float* gsm = reinterpret_cast<float*>(smem + Lay<HAS_BIAS>::SM_GATE) + il;
@@ -479,7 +480,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
       // prefetch the next item's length and this row's gate: consumed one iteration later
       if (idx + (int)gridDim.x < n_items) {
         cur.advance(a, step);
-        nxt = cur.load(a, lsm + (gbuf ^ 1), lane == 0);
+        nxt = cur.load(a, step, lsm + (gbuf ^ 1), lane == 0);
         prefetch_gate(nxt, gbuf ^ 1);
       }
       if (!it.valid) continue;
@@ -685,6 +686,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_consta
 int g_attention_variant = 1;
 // 1: two-tile clips use the paired item order (see Cursor); 0: query-tile-major order everywhere.
 int g_attention_paired = 1;
+// 1: clips are visited from the last one (the qkv rows the QKV GEMM wrote last are still in L2).
+int g_attention_reverse = 1;
 
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err) {
   if (a.D != a.H * HD) {
@@ -729,6 +732,7 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
   step.db = (grid % (a.B * a.H)) / a.H;
   step.dh = grid % a.H;
   step.paired = 0;
+  step.reverse = g_attention_reverse;
   if (g_attention_paired && ceil_div(a.slot, QT) == 2 && (grid & 1) == 0) {
     step.paired = 1;
     step.dq = 0;

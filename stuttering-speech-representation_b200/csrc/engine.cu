@@ -1947,6 +1947,14 @@ int ssr_tuning_set(const char* key, int32_t value) {
     g_pdl = value != 0;
     return 0;
   }
+  if (k == "attention_reverse") {
+    g_attention_reverse = value != 0;
+    return 0;
+  }
+  if (k == "ln_reverse") {
+    g_ln_reverse = value != 0;
+    return 0;
+  }
   if (k == "attention_paired") {
     g_attention_paired = value != 0;
     return 0;

@@ -18,6 +18,7 @@ struct LayerNormArgs {
   long long ld_out32;
   bf16* out_bf16;
   long long ld_out16;
+  int reverse;  // 1: CTAs walk the rows from the end (set by launch_layernorm from g_ln_reverse)
   // optional WavLM gate (needs head_dim 64)
   float* gate_out;  // [rows, n_heads]
   const float* gate_wa;
@@ -54,6 +55,8 @@ int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
 extern int g_attention_variant;  // attention_tc.cu kernel variant (process-wide tuning knob)
 extern int g_attention_paired;   // 1: paired item order for two-tile clips
+extern int g_attention_reverse;  // 1: clips are walked from the last one (freshest qkv rows first)
+extern int g_ln_reverse;         // 1: LayerNorm CTAs walk the rows from the end
 
 // Whisper decoder single-token cross-attention (decoder.cu). All token-level tensors have one row per clip.
 struct DecCrossArgs {

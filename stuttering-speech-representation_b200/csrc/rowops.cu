@@ -22,10 +22,13 @@ template <int NV, bool IN_BF16>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const LayerNormArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
+  // Rows are visited from the END of the matrix: the producer (a GEMM epilogue walking its M tiles upwards) wrote the
+  // last rows most recently, so the first CTAs find their fp32 input in L2 (the matrix is larger than L2), and the
+  // bf16 rows written last here are the ones the consuming GEMM reads first.
+  const long long row = a.reverse ? a.rows - 1 - ((long long)blockIdx.x * 8 + warp) : (long long)blockIdx.x * 8 + warp;
   ptx::griddep_wait();    // programmatic dependent launch: the rows come from the previous kernel
   ptx::griddep_launch();
-  if (row >= a.rows) return;
+  if (row >= a.rows || row < 0) return;
   constexpr int D = NV * 128;
   float v[NV][4];
   if (IN_BF16) {
@@ -128,8 +131,12 @@ layernorm_kernel(const LayerNormArgs a) {
   }
 }
 
-int launch_layernorm(const LayerNormArgs& a, cudaStream_t st, std::string& err) {
-  if (a.rows <= 0) return 0;
+int g_ln_reverse = 1;
+
+int launch_layernorm(const LayerNormArgs& a_in, cudaStream_t st, std::string& err) {
+  if (a_in.rows <= 0) return 0;
+  LayerNormArgs a = a_in;
+  a.reverse = g_ln_reverse;
   const int grid = (int)((a.rows + 7) / 8);
   const bool bf = a.in_bf16 != nullptr;
 #define SSR_LN_CASE(NV)                                                   \
