@@ -123,7 +123,8 @@ int32_t ssr_wavlm_rel_bucket(int32_t rel);
  * the variant they captured until the graph is dropped). Keys: "attention_variant" (bit 0: packed fp32 pair arithmetic
  * in the softmax; bit 1: a quarter of the exponentials on the FMA pipe; the default, 1, is the fastest measured),
  * "attention_paired" (1, default: clips of two query tiles are walked so that both tiles of a (clip, head) run at the
- * same time on neighbouring CTAs and K / V are read from HBM once; 0: query-tile-major order), "pdl" (1: the per-layer kernels
+ * same time on neighbouring CTAs and K / V are read from HBM once; 0: query-tile-major order), "attention_grouped" (the
+ * same for clips of three or more query tiles: the query tile is the fastest digit of the item index), "pdl" (1: the per-layer kernels
  * are launched with programmatic stream serialization so that a kernel's prologue overlaps its predecessor's tail;
  * 0, default: plain stream order — measured faster), "ln_reverse" / "attention_reverse" (1, default: LayerNorm rows /
  * attention clips are visited from the end, where the producing kernel's most recent output still sits in L2). Returns 0, or -1 for an unknown key. */

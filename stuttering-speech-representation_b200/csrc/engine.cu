@@ -1959,6 +1959,10 @@ int ssr_tuning_set(const char* key, int32_t value) {
     g_attention_paired = value != 0;
     return 0;
   }
+  if (k == "attention_grouped") {
+    g_attention_grouped = value != 0;
+    return 0;
+  }
   return -1;
 }
 

@@ -55,6 +55,7 @@ int launch_attention(const AttentionArgs& a, cudaStream_t st, std::string& err);
 int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& err);   // tcgen05 / TMEM / TMA
 extern int g_attention_variant;  // attention_tc.cu kernel variant (process-wide tuning knob)
 extern int g_attention_paired;   // 1: paired item order for two-tile clips
+extern int g_attention_grouped;  // 1: grouped item order for clips of three or more query tiles
 extern int g_attention_reverse;  // 1: clips are walked from the last one (freshest qkv rows first)
 extern int g_ln_reverse;         // 1: LayerNorm CTAs walk the rows from the end
 

@@ -279,3 +279,94 @@ def test_product_bucket_function_bit_exact_vs_hf():
         assert lib.ssr_wavlm_rel_bucket(r) == b, r
     lut = np.array([lib.ssr_wavlm_rel_bucket(r) for r in range(-148, 149)], dtype=np.int16)
     assert hashlib.sha256(lut.tobytes()).hexdigest().startswith("67859a4d9be1a425")
+
+
+_CURSOR_HARNESS = r"""
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#define __device__
+#define __forceinline__ inline
+struct { int x; } blockIdx;
+struct AttentionArgs { int B, slot, H, D; };
+constexpr int QT = 128;
+struct ItemPre { int b, h, q0; };
+%s
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+// host side of launch_attention_tc (attention_tc.cu): keep in step with it
+static Step make_step(const AttentionArgs& a, int grid, int paired, int grouped) {
+  Step step;
+  step.dq = grid / (a.B * a.H);
+  step.db = (grid %% (a.B * a.H)) / a.H;
+  step.dh = grid %% a.H;
+  step.paired = 0;
+  step.grouped = 0;
+  step.reverse = 0;
+  if (paired && ceil_div(a.slot, QT) == 2 && (grid & 1) == 0) {
+    step.paired = 1;
+    step.dq = 0;
+    step.db = (grid / 2) / a.H;
+    step.dh = (grid / 2) %% a.H;
+  } else if (grouped && ceil_div(a.slot, QT) >= 3) {
+    const int nqt = ceil_div(a.slot, QT);
+    step.grouped = nqt;
+    step.dq = grid %% nqt;
+    step.dh = (grid / nqt) %% a.H;
+    step.db = grid / (nqt * a.H);
+  }
+  return step;
+}
+int main(int argc, char** argv) {
+  AttentionArgs a;
+  a.B = atoi(argv[1]); a.slot = atoi(argv[2]); a.H = atoi(argv[3]); a.D = a.H * 64;
+  const int sms = atoi(argv[4]), paired = atoi(argv[5]), grouped = atoi(argv[6]);
+  const int nqt = ceil_div(a.slot, QT);
+  const long long items = (long long)nqt * a.H * a.B;
+  const int grid = (int)(items < 2LL * sms ? items : 2LL * sms);
+  const Step st = make_step(a, grid, paired, grouped);
+  std::vector<int> seen(items, 0);
+  long long adjacent = 0;  // items of one (clip, head) that run in the same round on consecutive CTAs
+  for (int c = 0; c < grid; ++c) {
+    blockIdx.x = c;
+    Cursor cur;
+    cur.init(a, st);
+    for (long long idx = c; idx < items; idx += grid) {
+      if (cur.qt < 0 || cur.qt >= nqt || cur.b < 0 || cur.b >= a.B || cur.h < 0 || cur.h >= a.H) {
+        printf("out of range: cta %%d idx %%lld -> qt %%d b %%d h %%d\n", c, idx, cur.qt, cur.b, cur.h);
+        return 1;
+      }
+      ++seen[((long long)cur.b * a.H + cur.h) * nqt + cur.qt];
+      if (idx + grid < items) cur.advance(a, st);
+    }
+  }
+  for (long long i = 0; i < items; ++i)
+    if (seen[i] != 1) { printf("item %%lld visited %%d times\n", i, seen[i]); return 1; }
+  printf("ok mode %%d\n", st.paired ? 1 : st.grouped ? 2 : 0);
+  return 0;
+}
+"""
+
+
+def test_attention_item_orders_visit_every_item_once(tmp_path):
+    """The persistent attention CTAs walk their items with the mixed-radix Cursor of csrc/attention_tc.cu (no division
+    per item). Its three orders (query-tile-major, paired, grouped) are compiled for the host from the product's own
+    source text and must each visit every (clip, head, query tile) exactly once, for grids smaller and larger than
+    the item count."""
+    src = open(os.path.join(ROOT, "stuttering-speech-representation_b200", "csrc", "attention_tc.cu")).read()
+    m = re.search(r"struct Step \{.*?\n\};\n", src, re.S)
+    c0 = src.index("struct Cursor {")
+    c1 = src.index("  // The clip length of the item goes global", c0)
+    code = _CURSOR_HARNESS % (m.group(0) + src[c0:c1] + "};\n")
+    (tmp_path / "cursor.cpp").write_text(code)
+    exe = str(tmp_path / "cursor")
+    subprocess.run(["g++", "-O1", "-o", exe, str(tmp_path / "cursor.cpp")], check=True)
+    modes = set()
+    for B, slot, H in [(64, 1500, 20), (1, 1500, 20), (3, 1500, 6), (5, 300, 4), (7, 385, 3), (256, 150, 16),
+                       (9, 256, 16), (40, 128, 16), (2, 150, 2), (33, 640, 12), (1, 1500, 1)]:
+        for sms in (148, 7, 1):
+            for paired, grouped in [(0, 0), (1, 0), (0, 1), (1, 1)]:
+                r = subprocess.run([exe, str(B), str(slot), str(H), str(sms), str(paired), str(grouped)],
+                                   capture_output=True, text=True)
+                assert r.returncode == 0, (B, slot, H, sms, paired, grouped, r.stdout)
+                modes.add(r.stdout.strip())
+    assert modes == {"ok mode 0", "ok mode 1", "ok mode 2"}

@@ -222,6 +222,42 @@ def test_attention(slot, H, lens, bias, impl):
             assert err < 2e-2, f"variant {variant}, clip {b}: max err {err}"
 
 
+@pytest.mark.parametrize("B,slot,H,bias", [(40, 640, 4, False), (24, 385, 6, True), (64, 300, 5, True)])
+def test_attention_item_orders_bit_identical(B, slot, H, bias):
+    """More items than resident CTAs and three or more query tiles per clip: the persistent CTAs walk the item list
+    either query-tile-major or grouped (all tiles of a (clip, head) on neighbouring CTAs at the same time, knob
+    "attention_grouped"). The work per item is the same, so the outputs must be bit-identical, and right."""
+    lib = _lib()
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(B + slot)
+    qkv = torch.randn(B * slot, 3 * D, device="cuda", generator=g)
+    qkv[:, :D] *= 0.25
+    qkv = qkv.bfloat16()
+    lens = [max(1, slot - 37 * i % slot) for i in range(B)]
+    lens[0], lens[-1] = slot, 1
+    lens_t = torch.tensor(lens, device="cuda", dtype=torch.int32)
+    R = 2048
+    gate = relb = None
+    if bias:
+        gate = torch.rand(B * slot, H, device="cuda", generator=g) * 2 + 0.5
+        relb = torch.randn(H, 2 * R - 1, device="cuda", generator=g)
+    outs = []
+    for grouped in (0, 1):
+        assert lib.ssr_tuning_set(b"attention_grouped", grouped) == 0
+        out = torch.zeros(B * slot, D, device="cuda", dtype=torch.bfloat16)
+        e = _err()
+        rc = lib.ssr_attention(qkv.data_ptr(), out.data_ptr(), B, slot, H, lens_t.data_ptr(), _ptr(gate), _ptr(relb),
+                               2 * R - 1, R - 1, 0, None, e, 512)
+        torch.cuda.synchronize()
+        lib.ssr_tuning_set(b"attention_grouped", 1)
+        assert rc == 0, e.value.decode()
+        outs.append(out)
+    live = (torch.arange(slot, device="cuda")[None, :] < lens_t[:, None]).reshape(-1)
+    assert torch.equal(outs[0][live], outs[1][live])
+    ref = _attn_ref(qkv, B, slot, H, lens_t, gate, relb, R - 1)
+    assert (outs[1].float() - ref)[live].abs().max().item() < 2e-2
+
+
 @pytest.mark.parametrize("scale", [1.0, 6.0, 40.0])
 def test_attention_stale_reference_and_rescale(scale):
     """Non-bias path (Whisper): O accumulates in TMEM against the block-0 reference maximum. Scores that keep rising
