@@ -208,6 +208,30 @@ struct Cursor {
     return p;
   }
 };
+// Host side of the item walk: gridDim.x decomposed in the mixed radix of the chosen order (tests/test_host_cpu.py
+// compiles Step, Cursor and this function for the host and checks that every item is visited exactly once).
+static Step make_step(const AttentionArgs& a, int grid, int paired, int grouped, int reverse) {
+  const int nqt = (a.slot + QT - 1) / QT;
+  Step step;
+  step.dq = grid / (a.B * a.H);
+  step.db = (grid % (a.B * a.H)) / a.H;
+  step.dh = grid % a.H;
+  step.paired = 0;
+  step.grouped = 0;
+  step.reverse = reverse;
+  if (paired && nqt == 2 && (grid & 1) == 0) {
+    step.paired = 1;
+    step.dq = 0;
+    step.db = (grid / 2) / a.H;
+    step.dh = (grid / 2) % a.H;
+  } else if (grouped && nqt >= 3) {
+    step.grouped = nqt;
+    step.dq = grid % nqt;
+    step.dh = (grid / nqt) % a.H;
+    step.db = grid / (nqt * a.H);
+  }
+  return step;
+}
 __device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -756,25 +780,7 @@ int launch_attention_tc(const AttentionArgs& a, cudaStream_t st, std::string& er
     return -1;
   }
   const int grid = (int)(items < 2LL * num_sms ? items : 2LL * num_sms);
-  Step step;
-  step.dq = grid / (a.B * a.H);
-  step.db = (grid % (a.B * a.H)) / a.H;
-  step.dh = grid % a.H;
-  step.paired = 0;
-  step.grouped = 0;
-  step.reverse = g_attention_reverse;
-  if (g_attention_paired && ceil_div(a.slot, QT) == 2 && (grid & 1) == 0) {
-    step.paired = 1;
-    step.dq = 0;
-    step.db = (grid / 2) / a.H;
-    step.dh = (grid / 2) % a.H;
-  } else if (g_attention_grouped && ceil_div(a.slot, QT) >= 3) {
-    const int nqt = ceil_div(a.slot, QT);
-    step.grouped = nqt;
-    step.dq = grid % nqt;
-    step.dh = (grid / nqt) % a.H;
-    step.db = grid / (nqt * a.H);
-  }
+  const Step step = make_step(a, grid, g_attention_paired, g_attention_grouped, g_attention_reverse);
   const int bsel = a.gate != nullptr ? 1 : 0;
   const int var = g_attention_variant & 3;
   launch_pdl(kern[bsel][var], dim3(grid), dim3(192), bsel ? Lay<true>::SMEM : Lay<false>::SMEM, st, tmq, tmkv, a,

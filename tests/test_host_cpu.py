@@ -293,29 +293,6 @@ constexpr int QT = 128;
 struct ItemPre { int b, h, q0; };
 %s
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
-// host side of launch_attention_tc (attention_tc.cu): keep in step with it
-static Step make_step(const AttentionArgs& a, int grid, int paired, int grouped) {
-  Step step;
-  step.dq = grid / (a.B * a.H);
-  step.db = (grid %% (a.B * a.H)) / a.H;
-  step.dh = grid %% a.H;
-  step.paired = 0;
-  step.grouped = 0;
-  step.reverse = 0;
-  if (paired && ceil_div(a.slot, QT) == 2 && (grid & 1) == 0) {
-    step.paired = 1;
-    step.dq = 0;
-    step.db = (grid / 2) / a.H;
-    step.dh = (grid / 2) %% a.H;
-  } else if (grouped && ceil_div(a.slot, QT) >= 3) {
-    const int nqt = ceil_div(a.slot, QT);
-    step.grouped = nqt;
-    step.dq = grid %% nqt;
-    step.dh = (grid / nqt) %% a.H;
-    step.db = grid / (nqt * a.H);
-  }
-  return step;
-}
 int main(int argc, char** argv) {
   AttentionArgs a;
   a.B = atoi(argv[1]); a.slot = atoi(argv[2]); a.H = atoi(argv[3]); a.D = a.H * 64;
@@ -323,7 +300,7 @@ int main(int argc, char** argv) {
   const int nqt = ceil_div(a.slot, QT);
   const long long items = (long long)nqt * a.H * a.B;
   const int grid = (int)(items < 2LL * sms ? items : 2LL * sms);
-  const Step st = make_step(a, grid, paired, grouped);
+  const Step st = make_step(a, grid, paired, grouped, 0);
   std::vector<int> seen(items, 0);
   long long adjacent = 0;  // items of one (clip, head) that run in the same round on consecutive CTAs
   for (int c = 0; c < grid; ++c) {
@@ -356,7 +333,9 @@ def test_attention_item_orders_visit_every_item_once(tmp_path):
     m = re.search(r"struct Step \{.*?\n\};\n", src, re.S)
     c0 = src.index("struct Cursor {")
     c1 = src.index("  // The clip length of the item goes global", c0)
-    code = _CURSOR_HARNESS % (m.group(0) + src[c0:c1] + "};\n")
+    f0 = src.index("static Step make_step(")
+    f1 = src.index("\n}\n", f0) + 3
+    code = _CURSOR_HARNESS % (m.group(0) + src[c0:c1] + "};\n" + src[f0:f1])
     (tmp_path / "cursor.cpp").write_text(code)
     exe = str(tmp_path / "cursor")
     subprocess.run(["g++", "-O1", "-o", exe, str(tmp_path / "cursor.cpp")], check=True)
