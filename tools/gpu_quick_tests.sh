@@ -1,6 +1,6 @@
 #!/bin/bash
-# short GPU slot: model tests other than Whisper's (those ran in the previous slot)
+# short GPU slot: the attention / pooling kernel tests on the current build
 mkdir -p gpurun_out
-timeout 100 python -m pytest tests/test_models_gpu.py -x -q -k "not whisper" > gpurun_out/quick_tests3.log 2>&1
-echo "exit $?" >> gpurun_out/quick_tests3.log
-tail -6 gpurun_out/quick_tests3.log
+timeout 30 python -m pytest tests/test_kernels_gpu.py -x -q -k "attention or pool" > gpurun_out/quick_tests4.log 2>&1
+echo "exit $?" >> gpurun_out/quick_tests4.log
+tail -4 gpurun_out/quick_tests4.log
